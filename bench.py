@@ -1,0 +1,343 @@
+#!/usr/bin/env python
+"""bench.py -- training frames/sec of the TIMIT-shape BLSTM (BASELINE.json configs[1]) on N B200s of one node.
+
+    python bench.py --gpus 1 --steps 20 --warmup 3                      (N>1: launched under torch.distributed.run)
+    python bench.py --impl reference --gpus 1 --steps 4 --warmup 1       (the reference's own CPU path, rank 0 only)
+
+A "step" is one pass of the hot path over one fraction (S parallel sequences per GPU): loadSequences (H2D) ->
+forward -> error -> backward -> per-layer gradient all-reduce (N>1) -> SGD+momentum update.
+  value : valid frames/s with the fraction already resident in HBM (CUDA-event time of forward..update, summed over K steps)
+  e2e   : valid frames/s through the host C ABI with HOST (pinned) buffers: H2D of the fraction and D2H of the objective
+          inside the timed region; K steps bracketed by barrier + synchronize, max over ranks
+  roofline / kernel_classes : per-kernel-class device time measured live with CUDA events on the launch stream
+  cpu_baseline : the reference's CPU path (oracle/_ref, built from /root/reference) on 1 host core, bounded sample
+Synthetic data: frames N(0,1), weights U(-0.1,0.1), lengths clip(lognormal(ln 290, .35), 90, 780), lr 1e-4, momentum .9.
+"""
+import argparse
+import ctypes
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (ROOT, os.path.join(ROOT, "lstm-rnn_b200", "python")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import synth  # noqa: E402
+
+METRIC, UNIT = "train_frames_per_sec", "frames/s"
+WORKLOAD = {
+    "C2": "C2 TIMIT-shape deep BLSTM: input 123 -> 3 x blstm 500 (250 cells/direction) -> softmax 183 -> multiclass CE, "
+          "parallel_sequences=100 per GPU, synthetic frames, lengths clip(lognormal(ln290,.35),90,780)",
+}
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        d = json.load(open(path))
+        return {"hbm_gbs": float(d["hbm_gbs"]), "bf16_tflops": float(d["bf16_tflops"]),
+                "bf16_tflops_sustained": float(d.get("bf16_tflops_sustained", d["bf16_tflops"])), "source": "measured"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed regions run."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.stop_flag = index, [], False
+
+    def run(self):
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.samples.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def summary(self):
+        self.stop_flag = True
+        sm = [float(s[0]) for s in self.samples if s[0].replace(".", "").isdigit()]
+        mx = [float(s[1]) for s in self.samples if s[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for s in self.samples for i in range(4) if len(s) >= 7 and s[3 + i].lower().startswith("active")})
+        busy = [x for x in sm if mx and x > 0.5 * mx[0]] or sm
+        return {"sm_mhz": float(np.median(busy)) if busy else None, "sm_max_mhz": mx[0] if mx else None, "reasons": reasons,
+                "samples": len(self.samples)}
+
+
+# ------------------------------------------------------------------------------------------- workload
+def c2_sequences(num_seqs, seed=2):
+    cfg = synth.config("C2")
+    lengths = synth.sequence_lengths(cfg, num_seqs, seed)
+    xs, cs, _ = synth.make_sequences(lengths, 123, seed, classes=183)
+    return cfg, lengths, xs, cs
+
+
+def layer_shapes(net_json):
+    layers = json.loads(net_json)["layers"]
+    return [(ly["type"], ly["size"], layers[i - 1]["size"] if i else 0) for i, ly in enumerate(layers)]
+
+
+def algorithmic_work(net_json, slots):
+    """Per fraction of `slots` pattern slots: HBM bytes of the recurrent kernels, flops of the GEMMs."""
+    fwd_b = bwd_b = flops = 0.0
+    first = True
+    for t, L, P in layer_shapes(net_json):
+        if t in ("blstm", "lstm"):
+            ndir = 2 if t == "blstm" else 1
+            fwd_b += 40.0 * L * slots            # read 4 pre-acts, write 4 acts + c + h
+            bwd_b += 48.0 * L * slots            # read 4 acts + c + c_prev + e, write 4 deltas + eps_c
+            H = L // ndir
+            flops += slots * (8.0 * L * P + (0 if first else 8.0 * L * P) + 8.0 * L * P + 8.0 * L * H)   # proj, input-err, dW_in, dW_rec
+            first = False
+        elif t.startswith("feedforward") or t == "softmax":
+            flops += slots * 6.0 * L * P
+    return fwd_b, bwd_b, flops
+
+
+# ------------------------------------------------------------------------------------------- reference arm / cpu baseline
+def cpu_reference_rate(steps, warmup, S=8, T=40, seed=2):
+    """The reference's own CPU path (NeuralNetwork<Cpu>, --cuda false) on a bounded sample of the C2 workload."""
+    from oracle import pyoracle
+    cfg = synth.config("C2")
+    net_json = cfg["net"]
+    kind = "reference" if pyoracle.ref_available() else "port"
+    rng = np.random.default_rng(seed)
+    lengths = np.clip(np.round(rng.lognormal(np.log(0.8 * T), 0.25, S)), 4, T).astype(int)
+    lengths[-1] = T
+    xs, cs, _ = synth.make_sequences(lengths, 123, seed, classes=183)
+    frac = pyoracle.make_fraction(xs, S, 0, seq_classes=cs, O=183)
+    net = (pyoracle.RefNet if kind == "reference" else pyoracle.OracleNet)(net_json, S, T)
+    for i, w in enumerate(synth.init_weights(net_json, seed + 1)):
+        if len(w):
+            net.set_weights(i, w)
+    times = []
+    for it in range(warmup + steps):
+        t0 = time.perf_counter()
+        net.load_fraction(frac)
+        net.forward()
+        net.calculate_error()
+        net.count_correct()
+        net.backward()
+        if it >= warmup:
+            times.append(time.perf_counter() - t0)
+    total = sum(times)
+    sample = ("C2 network, one fraction S=%d T=%d (%d valid frames of %d slots), %d passes of loadSequences+forward+error+backward "
+              "(SGD update excluded: 3.85M weights, <1%% of the step)" % (S, T, frac.valid_frames, frac.N, steps))
+    return {"value": frac.valid_frames * steps / total, "unit": UNIT, "cores": 1, "kind": kind, "sample": sample,
+            "ms_per_step": 1e3 * total / steps, "frames_per_step": frac.valid_frames}
+
+
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    steps = args.steps
+    base = cpu_reference_rate(steps, max(1, min(args.warmup, 2)))
+    line = {"impl": "reference", "metric": METRIC, "value": base["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+            "warmup": args.warmup, "ms_per_step": base["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic", "config": {"workload": WORKLOAD["C2"], "reference_sample": base["sample"]},
+            "cpu_baseline": {k: base[k] for k in ("value", "unit", "cores", "kind", "sample")},
+            "e2e": {"value": base["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------- our arm
+def run_ours(args, rank, world, local_rank):
+    import torch
+    import currennt_b200 as cb
+
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    stream = torch.cuda.Stream()
+    ctx = cb.Context(local_rank, stream.cuda_stream)
+    if args.mode == "fast":
+        ctx.set_gemm_mode(1)
+    k, h = cb.libs()
+
+    K, W = args.steps, args.warmup
+    cfg, lengths, xs, cs = c2_sequences((K + W) * 100 * world)
+    S = cfg["S"]
+    net_json = cfg["net"]
+    ds = cb.DataSet(ctx, xs, S, seq_classes=cs, O=183, truncate=cfg["truncate"], training=True, rank=rank, world=world)
+    del xs, cs
+    net = cb.Net(ctx, net_json, S, ds.max_len)
+    for i, w in enumerate(synth.init_weights(net_json, 3)):
+        if len(w):
+            net.set_weights(i, w)
+    comm = None
+    if world > 1:
+        idbuf = torch.zeros(128, dtype=torch.uint8)
+        if rank == 0:
+            raw = (ctypes.c_ubyte * 128)()
+            assert k.bl_comm_unique_id(raw) == 0, k.bl_last_error(None)
+            idbuf = torch.tensor(list(raw), dtype=torch.uint8)
+        idbuf = idbuf.cuda()
+        dist.broadcast(idbuf, 0)
+        raw = (ctypes.c_ubyte * 128)(*idbuf.cpu().tolist())
+        cp = ctypes.c_void_p()
+        ctx.check(k.bl_comm_create(ctx.p, rank, world, raw, ctypes.byref(cp)))
+        comm = cp
+        net.set_comm(comm)
+    opt = cb.Optimizer(net, 1e-4, 0.9, hybrid=True)
+
+    fracs = []
+    while True:
+        f = ds.next_fraction()
+        if f is None:
+            break
+        fracs.append(f)
+    order = np.random.default_rng(5).permutation(len(fracs))       # shuffle_fractions=true (examples/phoneme_recognition_timit/config.cfg)
+    fracs = [fracs[i] for i in order]
+    warm, timed = fracs[:W], fracs[W:W + K]
+    assert len(timed) == K, "not enough fractions"
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    with torch.cuda.stream(stream):
+        for f in warm:
+            opt.train_fraction(f)
+        barrier()
+
+        sampler = ClockSampler(local_rank)
+        if rank == 0:
+            sampler.start()
+
+        # ---- pass 1: fraction resident in HBM; per-class kernel times from the library's event brackets
+        k.bl_ctx_timing_enable(ctx.p, 1)
+        ms = (ctypes.c_double * 4)()
+        cnt = (ctypes.c_long * 4)()
+        k.bl_ctx_timing_read(ctx.p, ms, cnt)                       # reset
+        dev_ms = 0.0
+        for f in timed:
+            net.load_fraction(f)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            net.forward()
+            net.calculate_error()
+            net.count_correct()
+            net.backward()
+            opt.update_weights()
+            e1.record(stream)
+            torch.cuda.synchronize()
+            dev_ms += e0.elapsed_time(e1)
+        k.bl_ctx_timing_read(ctx.p, ms, cnt)
+        class_ms, class_cnt = [float(x) for x in ms], [int(x) for x in cnt]
+        k.bl_ctx_timing_enable(ctx.p, 0)
+
+        # ---- pass 2: end to end through the host ABI with pinned host buffers, K steps in one timed region
+        barrier()
+        l0 = ctx.launches
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        frames = 0
+        for f in timed:
+            _, _, n = opt.train_fraction(f)
+            frames += n
+        e1.record(stream)
+        barrier()
+        e2e_ms = e0.elapsed_time(e1)
+        launches = ctx.launches - l0
+        clocks = sampler.summary() if rank == 0 else None
+
+    tot = torch.tensor([float(frames), dev_ms, e2e_ms], dtype=torch.float64, device="cuda")
+    if dist is not None:
+        mx = tot.clone()
+        dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+        dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+        total_frames, dev_ms, e2e_ms = float(tot[0]), float(mx[1]), float(mx[2])
+    else:
+        total_frames = float(frames)
+
+    if rank == 0:
+        pk = peaks()
+        slots = sum(f.N for f in timed)
+        fwd_b, bwd_b, flops = algorithmic_work(net_json, slots)
+        names = ["gemm", "lstm_recurrent_fwd", "lstm_bptt", "elementwise"]
+        share = [m / max(sum(class_ms), 1e-9) for m in class_ms]
+        classes = {}
+        for i, nm in enumerate(names):
+            d = {"ms_per_step": class_ms[i] / K, "launch_groups_per_step": class_cnt[i] / K, "share_of_kernel_time": share[i]}
+            if nm == "gemm":
+                d.update(achieved_tflops=flops / (class_ms[i] * 1e-3) / 1e12 if class_ms[i] else None,
+                         frac_of_bf16_tensor_peak=(flops / (class_ms[i] * 1e-3) / 1e12) / pk["bf16_tflops_sustained"] if class_ms[i] else None)
+            if nm == "lstm_recurrent_fwd":
+                d.update(achieved_gbs=fwd_b / (class_ms[i] * 1e-3) / 1e9 if class_ms[i] else None)
+            if nm == "lstm_bptt":
+                d.update(achieved_gbs=bwd_b / (class_ms[i] * 1e-3) / 1e9 if class_ms[i] else None)
+            classes[nm] = d
+        # dominant kernel = the persistent recurrent kernels (forward + BPTT), bounded by HBM per SURVEY.md 8d
+        rec_ms = class_ms[1] + class_ms[2]
+        n_launch = class_cnt[1] + class_cnt[2]
+        achieved = (fwd_b + bwd_b) / (rec_ms * 1e-3) / 1e9
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "recurrent_traffic.json")
+        if os.path.exists(tpath):
+            traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
+        roofline = {"kernel": "lstm_{fwd,bwd}_persistent_kernel", "bound": "hbm", "achieved": achieved, "peak": pk["hbm_gbs"], "unit": "GB/s",
+                    "frac": achieved / pk["hbm_gbs"], "peak_source": pk["source"], "traffic": traffic,
+                    "algorithmic_bytes_per_launch": (fwd_b + bwd_b) / max(n_launch, 1), "avg_launch_ms": rec_ms / max(n_launch, 1),
+                    "share_of_kernel_time": share[1] + share[2]}
+        h2d = sum(f.N * (123 * 4 + 4) for f in timed) / K + sum(f.N for f in timed) / K * len(layer_shapes(net_json))
+        base = cpu_reference_rate(4, 1) if world == 1 else None
+        line = {"metric": METRIC, "value": total_frames / (dev_ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+                "ms_per_step": e2e_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+                "data": "synthetic",
+                "config": {"workload": WORKLOAD["C2"], "parallel_sequences_per_gpu": S, "gemm_mode": args.mode,
+                           "frames_per_step": total_frames / K, "slots_per_step_per_gpu": slots / K,
+                           "l2": "inputs larger than L2: every step touches ~%.1f GB of activations/deltas per GPU" % (slots / K * 2000 * 4 * 2 * 3 / 1e9),
+                           "plan": net.plan_info(2)},
+                "e2e": {"value": total_frames / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 8},
+                "device_ms_per_step": dev_ms / K, "gpu_launches": launches, "clocks": clocks, "roofline": roofline,
+                "kernel_classes": classes}
+        if base:
+            line["cpu_baseline"] = {kk: base[kk] for kk in ("value", "unit", "cores", "kind", "sample")}
+        print(json.dumps(line), flush=True)
+
+    if comm is not None:
+        k.bl_comm_destroy(comm)
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--mode", default="strict", choices=["strict", "fast"])
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    local_rank = int(os.environ.get("LOCAL_RANK", 0))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+    if args.warmup < 3:
+        args.warmup = 3
+    run_ours(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

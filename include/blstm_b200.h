@@ -1,0 +1,179 @@
+/*
+ * blstm_b200.h -- C ABI of the B200-native (sm_100a) LSTM/BLSTM training hot path.
+ *
+ * This is the drop-in boundary: the reference (CURRENNT, naxingyu/lstm-rnn) has no plugin or FFI
+ * interface, so the seam is the one its layer classes already have -- they call helpers::Matrix
+ * (cuBLAS) and Thrust functors.  Each entry point below replaces one of those call groups; the
+ * comment on each names the reference lines it replaces (paths relative to currennt_lib/src).
+ * INTEGRATION.md shows the binding a reference maintainer would add.
+ *
+ * Conventions
+ *   - extern "C", plain pointers and sizes, opaque handles; no C++/torch types.
+ *   - every function returns 0 on success, non-zero on failure and never throws;
+ *     bl_last_error(ctx) (ctx may be NULL for creation failures) returns the message.  The host
+ *     wrapper turns non-zero into std::runtime_error, the reference's error convention
+ *     (helpers/cublas.cu:44-45, main.cpp:492-495).
+ *   - all tensor pointers are DEVICE pointers unless the name says host; the caller owns them
+ *     (the reference's layers own outputs/outputErrors/weights, layers/Layer.cpp:41-67).
+ *   - work is enqueued on the context's stream and is asynchronous; bl_sync() waits.
+ *   - pattern-major layouts exactly as the reference: slot n = t*S + s, features fastest
+ *     (data_sets/DataSet.cpp:358).  Every [N][size] tensor takes a leading dimension `ld >= size`
+ *     (in floats) so callers may pad rows to 16 bytes for the TMA-fed tensor-core path; the
+ *     reference layout is ld == size.
+ *   - weights / weightUpdates use the reference's flat per-layer layout unchanged
+ *     (layers/LstmLayer.cu:535-541,583-596; layers/FeedForwardLayer.cu:149-165).
+ *   - there is no CPU fallback: without a CUDA device every call fails.
+ */
+#ifndef BLSTM_B200_H
+#define BLSTM_B200_H
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct bl_ctx       bl_ctx;        /* device + stream + scratch               */
+typedef struct bl_lstm_plan bl_lstm_plan;  /* per-layer workspace + launch geometry   */
+typedef struct bl_comm      bl_comm;       /* NCCL communicator for data parallelism  */
+
+/* GEMM precision modes (north_star: strict fp32 <= 1e-5, optional TF32/bf16 projection <= 2e-3) */
+#define BL_GEMM_STRICT   0   /* fp32-exact products: SIMT FFMA, or 3xTF32 error-compensated tcgen05 */
+#define BL_GEMM_FAST     1   /* single-pass TF32 tcgen05                                            */
+
+/* activation selectors of layers::FeedForwardLayer (LayerFactory.cu:54-61) */
+#define BL_ACT_TANH      0
+#define BL_ACT_LOGISTIC  1
+#define BL_ACT_IDENTITY  2
+
+/* pattern types, Types.hpp:30-33 */
+#define BL_PATTYPE_NONE   0
+#define BL_PATTYPE_FIRST  1
+#define BL_PATTYPE_NORMAL 2
+#define BL_PATTYPE_LAST   3
+
+/* ------------------------------------------------------------------ context, memory */
+
+/* `stream` is a cudaStream_t (or NULL for a stream owned by the context).  Replaces the implicit
+ * default-stream / cublasCreate state of helpers/cublas.cu:37-58. */
+int  bl_ctx_create(int device, void *stream, bl_ctx **out);
+void bl_ctx_destroy(bl_ctx *ctx);
+const char *bl_last_error(const bl_ctx *ctx);
+int  bl_sync(bl_ctx *ctx);
+/* 0 = strict (default), 1 = fast; applies to the GEMMs issued by the layer-level calls */
+int  bl_ctx_set_gemm_mode(bl_ctx *ctx, int mode);
+int  bl_ctx_num_sms(const bl_ctx *ctx);
+/* number of kernels this library has launched on the context since creation (bench.py gpu_launches) */
+long bl_ctx_launch_count(const bl_ctx *ctx);
+
+/* Optional per-kernel-class device timing for bench.py's roofline line: when enabled, the library brackets its
+ * launches with CUDA events on the context's stream.  Classes: 0 gemm, 1 lstm recurrent forward (persistent),
+ * 2 lstm BPTT (persistent), 3 everything else (elementwise / reductions).  bl_ctx_timing_read synchronises the
+ * stream, returns accumulated milliseconds and launch counts per class, and resets the accumulators. */
+#define BL_TIMING_CLASSES 4
+int  bl_ctx_timing_enable(bl_ctx *ctx, int on);
+int  bl_ctx_timing_read(bl_ctx *ctx, double *ms4, long *count4);
+
+/* thrust::device_vector allocation / thrust::copy replacements (Types.hpp:58-67, layers/InputLayer.cpp:59) */
+int  bl_malloc(bl_ctx *ctx, void **ptr, size_t bytes);
+int  bl_free(bl_ctx *ctx, void *ptr);
+int  bl_memset(bl_ctx *ctx, void *ptr, int value, size_t bytes);
+int  bl_memcpy_h2d(bl_ctx *ctx, void *dst, const void *host_src, size_t bytes);
+int  bl_memcpy_d2h(bl_ctx *ctx, void *host_dst, const void *src, size_t bytes);
+int  bl_memcpy_d2d(bl_ctx *ctx, void *dst, const void *src, size_t bytes);
+/* strided row copies: `rows` rows of `row_bytes`, pitches in bytes (packed host <-> padded device) */
+int  bl_memcpy2d_h2d(bl_ctx *ctx, void *dst, size_t dst_pitch, const void *host_src, size_t src_pitch, size_t row_bytes, size_t rows);
+int  bl_memcpy2d_d2h(bl_ctx *ctx, void *host_dst, size_t dst_pitch, const void *src, size_t src_pitch, size_t row_bytes, size_t rows);
+/* pinned host memory for the fraction staging buffers */
+int  bl_malloc_host(bl_ctx *ctx, void **ptr, size_t bytes);
+int  bl_free_host(bl_ctx *ctx, void *ptr);
+
+/* ------------------------------------------------------------------ helpers::Matrix products
+ * Drop-in for cublas::multiplyMatrices (helpers/cublas.hpp:30-37, helpers/cublas.cu:60-88) and therefore
+ * for Matrix<Gpu>::assignProduct/addProduct (helpers/Matrix.cu:351-377): column-major,
+ *   C[m x n] (ldc) = op(A) * op(B) (+ C if accumulate),  op(A) is m x k, op(B) is k x n.
+ * (transA,transB) in {(1,0),(0,0),(0,1)}; (1,1) fails like the reference's "Not implemented". */
+int bl_gemm_f32(bl_ctx *ctx, int transA, int transB, int m, int n, int k,
+                const float *A, int lda, const float *B, int ldb, float *C, int ldc,
+                int accumulate, int mode);
+
+/* ------------------------------------------------------------------ LSTM / BLSTM layer
+ * Replaces LstmLayer<Gpu>'s constructor buffers (LstmLayer.cu:543-619), computeForwardPass (:763-886:
+ * 8 projection SGEMMs, 2*(T-1)*4 recurrent SGEMMs, 2*T ComputeBlockOutputFn launches, ResortOutputsFn)
+ * and computeBackwardPass (:888-1051: ResortOutputErrorsFn, 2*(T-1)*4 SGEMMs + 2*T ComputeBlockErrorsFn,
+ * 8 input-error SGEMMs, ComputeWeightUpdateFn).
+ *   P = preceding layer size, L = layer size (both directions), S = parallel sequences. */
+int    bl_lstm_plan_create(bl_ctx *ctx, int P, int L, int bidirectional, int S, int maxT, float bias, bl_lstm_plan **out);
+void   bl_lstm_plan_destroy(bl_lstm_plan *plan);
+size_t bl_lstm_num_weights(int P, int L, int bidirectional);          /* LstmLayer.cu:525 */
+
+/* X [T*S][ldx] preceding outputs, patTypes [T*S] chars, Y [T*S][ldy] layer outputs ([fw H | bw H] per row). */
+int bl_lstm_forward(bl_lstm_plan *plan, const float *W, const float *X, int ldx, const char *patTypes,
+                    int T, int Tmin, float *Y, int ldy);
+/* dY [T*S][lddy] this layer's outputErrors (for the unidirectional layer it is updated in place with the
+ * recurrent error terms, as the reference's vector swap does, LstmLayer.cu:907-910); dX [T*S][lddx] =
+ * preceding layer's outputErrors or NULL when that layer is not trainable (LstmLayer.cu:991-992);
+ * dW = weightUpdates (gradient sums, same layout as W).  Must follow bl_lstm_forward on the same fraction. */
+int bl_lstm_backward(bl_lstm_plan *plan, const float *W, const float *X, int ldx, const float *Y, int ldy,
+                     float *dY, int lddy, const char *patTypes, int T, int Tmin,
+                     float *dX, int lddx, float *dW);
+/* Gathers an internal tensor into the reference's [T*S][H] layout (LstmLayer.hpp:169-232 accessors):
+ * which: 0 cellStates 1 cellStateErrors 2 niActs 3 igActs 4 fgActs 5 ogActs 6 niDeltas 7 igDeltas 8 fgDeltas 9 ogDeltas */
+int bl_lstm_get_internal(bl_lstm_plan *plan, int dir, int which, int T, float *dst);
+/* Launch geometry chosen for the persistent kernels: out[0..3] = fwd {G seq groups, C cell slices, cells/CTA, smem bytes},
+ * out[4..7] = bwd likewise. */
+int bl_lstm_plan_info(const bl_lstm_plan *plan, int *out8);
+
+/* ------------------------------------------------------------------ feed-forward / softmax layers
+ * FeedForwardLayer<Gpu,TActFn>::computeForwardPass (FeedForwardLayer.cu:143-172): Y = act(W^T X + bias*b) for N slots */
+int bl_ff_forward(bl_ctx *ctx, int act, int P, int O, int N, float bias, const float *W,
+                  const float *X, int ldx, float *Y, int ldy);
+/* ...::computeBackwardPass (FeedForwardLayer.cu:174-224): dY <- act'(Y)*dY in place; dX = W*dY (NULL to skip);
+ * dW = [X*dY^T | bias*sum_n dY] */
+int bl_ff_backward(bl_ctx *ctx, int act, int P, int O, int N, float bias, const float *W,
+                   const float *X, int ldx, const float *Y, int ldy, float *dY, int lddy,
+                   float *dX, int lddx, float *dW);
+/* SoftmaxLayer's own part of the passes (SoftmaxLayer.cu:263-313 and :328-348), in place, padded patterns untouched */
+int bl_softmax_forward(bl_ctx *ctx, int O, int N, const char *patTypes, float *Y, int ldy);
+int bl_softmax_backward(bl_ctx *ctx, int O, int N, const char *patTypes, const float *Y, int ldy, float *dY, int lddy);
+
+/* ------------------------------------------------------------------ post-output layers
+ * MulticlassClassificationLayer: calculateError + countCorrectClassifications in one pass
+ * (MulticlassClassificationLayer.cu:159-177, 195-214); results land in DEVICE scalars. */
+int bl_multiclass_error(bl_ctx *ctx, int O, int N, const int *targetClasses, const float *Y, int ldy,
+                        float *d_error, int *d_correct);
+/* ...::computeBackwardPass (:221-240): zero-fill, then dY[n,target] = -1/max(FLT_MIN,y) */
+int bl_multiclass_backward(bl_ctx *ctx, int O, int N, const int *targetClasses, const float *Y, int ldy,
+                           float *dY, int lddy);
+/* CePostOutputLayer (CePostOutputLayer.cu:125-166) and SsePostOutputLayer (SsePostOutputLayer.cu:114-155) */
+int bl_ce_error(bl_ctx *ctx, int O, int N, const char *patTypes, const float *targets, int ldt,
+                const float *Y, int ldy, float *d_error);
+int bl_ce_backward(bl_ctx *ctx, int O, int N, const char *patTypes, const float *targets, int ldt,
+                   const float *Y, int ldy, float *dY, int lddy);
+int bl_sse_error(bl_ctx *ctx, int O, int N, const char *patTypes, const float *targets, int ldt,
+                 const float *Y, int ldy, float *d_error);
+int bl_sse_backward(bl_ctx *ctx, int O, int N, const char *patTypes, const float *targets, int ldt,
+                    const float *Y, int ldy, float *dY, int lddy);
+
+/* ------------------------------------------------------------------ optimizer step
+ * UpdateWeightFn (optimizers/SteepestDescentOptimizer.cu:39-59): delta = momentum*delta - lr*grad; w += delta */
+int bl_sgd_update(bl_ctx *ctx, size_t n, float learningRate, float momentum, float *W, const float *dW, float *deltas);
+/* batch-mode gradient accumulation over fractions, thrust::transform(plus) of optimizers/Optimizer.cu:77-80: y += x */
+int bl_vector_add(bl_ctx *ctx, size_t n, const float *x, float *y);
+
+/* ------------------------------------------------------------------ data parallelism (new)
+ * One communicator per process/GPU.  `unique_id` is the 128-byte ncclUniqueId produced by rank 0
+ * (bl_comm_unique_id) and distributed by the launcher (bench.py uses torch.distributed for that). */
+int  bl_comm_unique_id(void *id128);
+int  bl_comm_create(bl_ctx *ctx, int rank, int world, const void *id128, bl_comm **out);
+void bl_comm_destroy(bl_comm *comm);
+/* In-place sum over ranks of `count` floats on the communicator's side stream, ordered after the work
+ * already enqueued on the context's stream; returns immediately. */
+int  bl_allreduce_sum_f32(bl_comm *comm, float *buf, size_t count);
+/* Makes the context's stream wait for every all-reduce issued so far. */
+int  bl_comm_join(bl_comm *comm);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BLSTM_B200_H */

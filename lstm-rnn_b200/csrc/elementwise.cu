@@ -1,0 +1,392 @@
+// Feed-forward / softmax / post-output / optimizer kernels behind the C ABI.  All are HBM-bound streaming passes:
+// coalesced (feature index fastest across lanes), one warp per pattern where a row reduction is needed, and
+// deterministic two-stage reductions for the scalar objectives.
+#include "common.cuh"
+
+namespace bl {
+int gemm_f32_simt(bl_ctx *ctx, int transA, int transB, int m, int n, int k,
+                  const float *A, int lda, const float *B, int ldb, float *C, int ldc, int accumulate);
+
+template <int ACT> __device__ __forceinline__ float act_fn(float x)
+{ return ACT == BL_ACT_TANH ? tanh_fn(x) : ACT == BL_ACT_LOGISTIC ? logistic_fn(x) : x; }
+template <int ACT> __device__ __forceinline__ float act_deriv(float y)
+{ return ACT == BL_ACT_TANH ? tanh_deriv(y) : ACT == BL_ACT_LOGISTIC ? logistic_deriv(y) : 1.0f; }
+
+// ComputeOutputFn, FeedForwardLayer.cu:45-66
+template <int ACT>
+__global__ void ff_bias_act_kernel(int O, size_t total, float bias, const float *__restrict__ bw, float *__restrict__ Y, int ldy)
+{
+    for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
+        const size_t n = e / O; const int j = (int)(e % O);
+        float *p = Y + n * ldy + j;
+        *p = act_fn<ACT>(__fadd_rn(*p, __fmul_rn(bias, bw[j])));
+    }
+}
+
+// ComputeDeltaFn, FeedForwardLayer.cu:68-81 (all slots, padding included)
+template <int ACT>
+__global__ void ff_delta_kernel(int O, size_t total, const float *__restrict__ Y, int ldy, float *__restrict__ dY, int lddy)
+{
+    for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
+        const size_t n = e / O; const int j = (int)(e % O);
+        float *p = dY + n * lddy + j;
+        *p = __fmul_rn(act_deriv<ACT>(Y[n * ldy + j]), *p);
+    }
+}
+
+// ComputeBiasWeightUpdateFn, FeedForwardLayer.cu:83-102: column sums of bias*delta; grid (ceil(O/32), nsplit), block (32,8)
+__global__ void col_sum_kernel(int O, int N, float bias, const float *__restrict__ dY, int lddy, float *__restrict__ part, int rows_per_split)
+{
+    __shared__ float red[8][33];
+    const int col = blockIdx.x * 32 + threadIdx.x;
+    const int n0 = blockIdx.y * rows_per_split, n1 = min(N, n0 + rows_per_split);
+    float acc = 0.0f;
+    if (col < O)
+        for (int n = n0 + threadIdx.y; n < n1; n += 8) acc += bias * dY[(size_t)n * lddy + col];
+    red[threadIdx.y][threadIdx.x] = acc;
+    __syncthreads();
+    if (threadIdx.y == 0 && col < O) {
+        float s = 0.0f;
+        for (int y = 0; y < 8; ++y) s += red[y][threadIdx.x];
+        part[(size_t)blockIdx.y * O + col] = s;
+    }
+}
+
+__global__ void col_sum_finish_kernel(int O, int nsplit, const float *__restrict__ part, float *__restrict__ out)
+{
+    const int col = blockIdx.x * blockDim.x + threadIdx.x;
+    if (col >= O) return;
+    float s = 0.0f;
+    for (int z = 0; z < nsplit; ++z) s += part[(size_t)z * O + col];
+    out[col] = s;
+}
+
+__device__ __forceinline__ float warp_sum(float v) { for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o); return v; }
+__device__ __forceinline__ float warp_max(float v) { for (int o = 16; o; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o)); return v; }
+__device__ __forceinline__ float warp_min(float v) { for (int o = 16; o; o >>= 1) v = fminf(v, __shfl_xor_sync(0xffffffffu, v, o)); return v; }
+
+// SoftmaxLayer forward (SoftmaxLayer.cu:45-155, 263-313): one warp per pattern, 4 fused passes over the row.
+__global__ void softmax_fwd_kernel(int O, int N, const char *__restrict__ pat, float *__restrict__ Y, int ldy)
+{
+    const int lane = threadIdx.x & 31;
+    const int wpb = blockDim.x >> 5;
+    for (int n = blockIdx.x * wpb + (threadIdx.x >> 5); n < N; n += gridDim.x * wpb) {
+        if (pat[n] == BL_PATTYPE_NONE) continue;                       // padded patterns keep the raw activations
+        float *y = Y + (size_t)n * ldy;
+        float mx = BL_FLT_MIN, mn = BL_FLT_MAX;                        // CalculateOffsetFn initial values, :62-63
+        for (int i = lane; i < O; i += 32) { const float x = y[i]; mn = fminf(mn, x); mx = fmaxf(mx, x); }
+        mx = warp_max(mx); mn = warp_min(mn);
+        const float off = __fmul_rn(0.5f, __fadd_rn(mn, mx));
+        float sum = 0.0f;
+        for (int i = lane; i < O; i += 32) { const float v = safe_exp(__fsub_rn(y[i], off)); y[i] = v; sum += v; }
+        sum = warp_sum(sum);
+        for (int i = lane; i < O; i += 32) y[i] = __fdiv_rn(y[i], sum);
+    }
+}
+
+// SoftmaxLayer backward (SoftmaxLayer.cu:157-219, 328-348): e_i <- y_i*(e_i - sum_j y_j e_j)
+__global__ void softmax_bwd_kernel(int O, int N, const char *__restrict__ pat, const float *__restrict__ Y, int ldy,
+                                   float *__restrict__ dY, int lddy)
+{
+    const int lane = threadIdx.x & 31;
+    const int wpb = blockDim.x >> 5;
+    for (int n = blockIdx.x * wpb + (threadIdx.x >> 5); n < N; n += gridDim.x * wpb) {
+        if (pat[n] == BL_PATTYPE_NONE) continue;
+        const float *y = Y + (size_t)n * ldy; float *e = dY + (size_t)n * lddy;
+        float off = 0.0f;
+        for (int i = lane; i < O; i += 32) off += y[i] * e[i];
+        off = warp_sum(off);
+        for (int i = lane; i < O; i += 32) e[i] = __fmul_rn(y[i], __fsub_rn(e[i], off));
+    }
+}
+
+// MulticlassClassificationLayer::calculateError + countCorrectClassifications (MulticlassClassificationLayer.cu:48-104):
+// one warp per pattern; per-block partials (error sum, correct count), finished in block order.
+__global__ void multiclass_error_kernel(int O, int N, const int *__restrict__ tc, const float *__restrict__ Y, int ldy,
+                                        float *__restrict__ perr, int *__restrict__ pcor)
+{
+    __shared__ float serr[32]; __shared__ int scor[32];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+    float err = 0.0f; int cor = 0;
+    for (int n = blockIdx.x * wpb + w; n < N; n += gridDim.x * wpb) {
+        const int target = tc[n];
+        if (target == -1) continue;
+        const float *y = Y + (size_t)n * ldy;
+        // argmax with strict '>' from (0, class 0): first index of the maximum if it is > 0, else class 0 (:84-95)
+        float best = 0.0f; int est = 0;
+        for (int i = lane; i < O; i += 32) { const float o = y[i]; if (o > best) { best = o; est = i; } }
+        for (int s = 16; s; s >>= 1) {
+            const float ob = __shfl_xor_sync(0xffffffffu, best, s); const int oi = __shfl_xor_sync(0xffffffffu, est, s);
+            if (ob > best || (ob == best && oi < est)) { best = ob; est = oi; }
+        }
+        if (best <= 0.0f) est = 0;
+        if (lane == 0) {
+            err += logf(fmaxf(BL_FLT_MIN, y[target]));                 // :62-63
+            cor += (est == target);
+        }
+    }
+    if (lane == 0) { serr[w] = err; scor[w] = cor; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float e = 0.0f; int c = 0;
+        for (int i = 0; i < wpb; ++i) { e += serr[i]; c += scor[i]; }
+        perr[blockIdx.x] = e; pcor[blockIdx.x] = c;
+    }
+}
+
+__global__ void multiclass_error_finish_kernel(int nblocks, const float *__restrict__ perr, const int *__restrict__ pcor,
+                                               float *__restrict__ d_error, int *__restrict__ d_correct)
+{
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        float e = 0.0f; int c = 0;
+        for (int i = 0; i < nblocks; ++i) { e += perr[i]; c += pcor[i]; }
+        *d_error = -e;                                                 // :213
+        if (d_correct) *d_correct = c;
+    }
+}
+
+// MulticlassClassificationLayer::computeBackwardPass (:106-135, 221-240): fused fill-zero + scatter
+__global__ void multiclass_bwd_kernel(int O, size_t total, const int *__restrict__ tc, const float *__restrict__ Y, int ldy,
+                                      float *__restrict__ dY, int lddy)
+{
+    for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
+        const size_t n = e / O; const int j = (int)(e % O);
+        float v = 0.0f;
+        if (tc[n] == j) v = -__fdiv_rn(1.0f, fmaxf(BL_FLT_MIN, Y[n * ldy + j]));
+        dY[n * lddy + j] = v;
+    }
+}
+
+// CE / SSE objectives (CePostOutputLayer.cu:43-70, SsePostOutputLayer.cu:39-60): block partials
+template <bool CE>
+__global__ void dense_error_kernel(int O, size_t total, const char *__restrict__ pat, const float *__restrict__ tg, int ldt,
+                                   const float *__restrict__ Y, int ldy, float *__restrict__ part)
+{
+    __shared__ float red[32];
+    float acc = 0.0f;
+    for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
+        const size_t n = e / O; const int j = (int)(e % O);
+        if (pat[n] == BL_PATTYPE_NONE) continue;
+        const float t = tg[n * ldt + j], y = Y[n * ldy + j];
+        if (CE) {
+            const float ft = fmaxf(BL_FLT_MIN, t), o = fmaxf(BL_FLT_MIN, y);
+            acc += __fmul_rn(t, logf(__fdiv_rn(ft, o)));
+        } else {
+            const float diff = __fsub_rn(t, y);
+            acc += __fmul_rn(diff, diff);
+        }
+    }
+    acc = warp_sum(acc);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float s = 0.0f;
+        for (int i = 0; i < (int)(blockDim.x >> 5); ++i) s += red[i];
+        part[blockIdx.x] = s;
+    }
+}
+
+__global__ void dense_error_finish_kernel(int nblocks, float scale, const float *__restrict__ part, float *__restrict__ d_error)
+{
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        float s = 0.0f;
+        for (int i = 0; i < nblocks; ++i) s += part[i];
+        *d_error = scale * s;
+    }
+}
+
+// CePostOutputLayer.cu:72-98 / SsePostOutputLayer.cu:62-88
+template <bool CE>
+__global__ void dense_bwd_kernel(int O, size_t total, const char *__restrict__ pat, const float *__restrict__ tg, int ldt,
+                                 const float *__restrict__ Y, int ldy, float *__restrict__ dY, int lddy)
+{
+    for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
+        const size_t n = e / O; const int j = (int)(e % O);
+        float v = 0.0f;
+        if (pat[n] != BL_PATTYPE_NONE) {
+            const float t = tg[n * ldt + j], y = Y[n * ldy + j];
+            if (CE) { const float r = -__fdiv_rn(t, fmaxf(BL_FLT_MIN, y)); v = r < -100.0f ? -100.0f : (r > 100.0f ? 100.0f : r); }
+            else v = __fsub_rn(y, t);
+        }
+        dY[n * lddy + j] = v;
+    }
+}
+
+// UpdateWeightFn, optimizers/SteepestDescentOptimizer.cu:39-59
+__global__ void sgd_kernel(size_t n, float lr, float mom, float *__restrict__ W, const float *__restrict__ dW, float *__restrict__ dl)
+{
+    for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (size_t)gridDim.x * blockDim.x) {
+        const float delta = __fsub_rn(__fmul_rn(mom, dl[e]), __fmul_rn(lr, dW[e]));
+        dl[e] = delta;
+        W[e] = __fadd_rn(W[e], delta);
+    }
+}
+
+__global__ void vector_add_kernel(size_t n, const float *__restrict__ x, float *__restrict__ y)
+{
+    for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (size_t)gridDim.x * blockDim.x) y[e] = __fadd_rn(y[e], x[e]);
+}
+
+static inline int ew_blocks(bl_ctx *ctx, size_t total, int threads)
+{
+    size_t b = cdivz(total, threads);
+    const size_t cap = (size_t)ctx->num_sms * 16;
+    return (int)(b < 1 ? 1 : (b > cap ? cap : b));
+}
+
+} // namespace bl
+
+using namespace bl;
+
+extern "C" {
+
+int bl_ff_forward(bl_ctx *ctx, int act, int P, int O, int N, float bias, const float *W,
+                  const float *X, int ldx, float *Y, int ldy)
+{
+    if (ldx < P || ldy < O) return fail(ctx, "bl_ff_forward: leading dimension too small");
+    // outputsMatrix.assignProduct(weightsMatrix, true, plOutputsMatrix, false), FeedForwardLayer.cu:147-153
+    BL_CHECK(bl_gemm_f32(ctx, 1, 0, O, N, P, W, P, X, ldx, Y, ldy, 0, ctx->gemm_mode));
+    TimedRegion timed(ctx, 3);
+    const size_t total = (size_t)N * O;
+    const int blocks = ew_blocks(ctx, total, 256);
+    const float *bw = W + (size_t)O * P;
+    switch (act) {
+        case BL_ACT_TANH:     ff_bias_act_kernel<BL_ACT_TANH><<<blocks, 256, 0, ctx->stream>>>(O, total, bias, bw, Y, ldy); break;
+        case BL_ACT_LOGISTIC: ff_bias_act_kernel<BL_ACT_LOGISTIC><<<blocks, 256, 0, ctx->stream>>>(O, total, bias, bw, Y, ldy); break;
+        case BL_ACT_IDENTITY: ff_bias_act_kernel<BL_ACT_IDENTITY><<<blocks, 256, 0, ctx->stream>>>(O, total, bias, bw, Y, ldy); break;
+        default: return fail(ctx, "Unsupported activation function");
+    }
+    BL_LAUNCHED(ctx);
+    return 0;
+}
+
+int bl_ff_backward(bl_ctx *ctx, int act, int P, int O, int N, float bias, const float *W,
+                   const float *X, int ldx, const float *Y, int ldy, float *dY, int lddy,
+                   float *dX, int lddx, float *dW)
+{
+    if (ldx < P || ldy < O || lddy < O || (dX && lddx < P)) return fail(ctx, "bl_ff_backward: leading dimension too small");
+    const size_t total = (size_t)N * O;
+    const int blocks = ew_blocks(ctx, total, 256);
+    {
+    TimedRegion timed(ctx, 3);
+    switch (act) {
+        case BL_ACT_TANH:     ff_delta_kernel<BL_ACT_TANH><<<blocks, 256, 0, ctx->stream>>>(O, total, Y, ldy, dY, lddy); break;
+        case BL_ACT_LOGISTIC: ff_delta_kernel<BL_ACT_LOGISTIC><<<blocks, 256, 0, ctx->stream>>>(O, total, Y, ldy, dY, lddy); break;
+        case BL_ACT_IDENTITY: break;   // deriv == 1: delta == error, nothing to do
+        default: return fail(ctx, "Unsupported activation function");
+    }
+    if (act != BL_ACT_IDENTITY) BL_LAUNCHED(ctx);
+    }
+    // plErrorsMatrix.assignProduct(weightsMatrix, false, deltasMatrix, false), FeedForwardLayer.cu:190-197
+    if (dX) BL_CHECK(bl_gemm_f32(ctx, 0, 0, P, N, O, W, P, dY, lddy, dX, lddx, 0, ctx->gemm_mode));
+    // weightUpdatesMatrix.assignProduct(plOutputsMatrix, false, deltasMatrix, true), :200-207
+    BL_CHECK(bl_gemm_f32(ctx, 0, 1, P, O, N, X, ldx, dY, lddy, dW, P, 0, ctx->gemm_mode));
+    // bias weight updates, :210-223
+    int nsplit = 64, rows = cdiv(N, nsplit);
+    if (rows < 64) rows = 64;
+    nsplit = cdiv(N, rows);
+    BL_CHECK(ensure_scratch(ctx, (size_t)nsplit * O * sizeof(float)));
+    TimedRegion timed(ctx, 3);
+    col_sum_kernel<<<dim3(cdiv(O, 32), nsplit), dim3(32, 8), 0, ctx->stream>>>(O, N, bias, dY, lddy, ctx->scratch, rows);
+    BL_LAUNCHED(ctx);
+    col_sum_finish_kernel<<<cdiv(O, 256), 256, 0, ctx->stream>>>(O, nsplit, ctx->scratch, dW + (size_t)O * P);
+    BL_LAUNCHED(ctx);
+    return 0;
+}
+
+int bl_softmax_forward(bl_ctx *ctx, int O, int N, const char *patTypes, float *Y, int ldy)
+{
+    if (ldy < O) return fail(ctx, "bl_softmax_forward: leading dimension too small");
+    const int blocks = ew_blocks(ctx, (size_t)N * 32, 256);
+    TimedRegion timed(ctx, 3);
+    softmax_fwd_kernel<<<blocks, 256, 0, ctx->stream>>>(O, N, patTypes, Y, ldy);
+    BL_LAUNCHED(ctx);
+    return 0;
+}
+
+int bl_softmax_backward(bl_ctx *ctx, int O, int N, const char *patTypes, const float *Y, int ldy, float *dY, int lddy)
+{
+    if (ldy < O || lddy < O) return fail(ctx, "bl_softmax_backward: leading dimension too small");
+    const int blocks = ew_blocks(ctx, (size_t)N * 32, 256);
+    TimedRegion timed(ctx, 3);
+    softmax_bwd_kernel<<<blocks, 256, 0, ctx->stream>>>(O, N, patTypes, Y, ldy, dY, lddy);
+    BL_LAUNCHED(ctx);
+    return 0;
+}
+
+int bl_multiclass_error(bl_ctx *ctx, int O, int N, const int *targetClasses, const float *Y, int ldy,
+                        float *d_error, int *d_correct)
+{
+    if (ldy < O) return fail(ctx, "bl_multiclass_error: leading dimension too small");
+    int blocks = ew_blocks(ctx, (size_t)N * 32, 256); if (blocks > 1024) blocks = 1024;
+    BL_CHECK(ensure_scratch(ctx, (size_t)blocks * 2 * sizeof(float)));
+    float *perr = ctx->scratch; int *pcor = reinterpret_cast<int *>(ctx->scratch + blocks);
+    TimedRegion timed(ctx, 3);
+    multiclass_error_kernel<<<blocks, 256, 0, ctx->stream>>>(O, N, targetClasses, Y, ldy, perr, pcor);
+    BL_LAUNCHED(ctx);
+    multiclass_error_finish_kernel<<<1, 32, 0, ctx->stream>>>(blocks, perr, pcor, d_error, d_correct);
+    BL_LAUNCHED(ctx);
+    return 0;
+}
+
+int bl_multiclass_backward(bl_ctx *ctx, int O, int N, const int *targetClasses, const float *Y, int ldy, float *dY, int lddy)
+{
+    if (ldy < O || lddy < O) return fail(ctx, "bl_multiclass_backward: leading dimension too small");
+    const size_t total = (size_t)N * O;
+    TimedRegion timed(ctx, 3);
+    multiclass_bwd_kernel<<<ew_blocks(ctx, total, 256), 256, 0, ctx->stream>>>(O, total, targetClasses, Y, ldy, dY, lddy);
+    BL_LAUNCHED(ctx);
+    return 0;
+}
+
+static int dense_error(bl_ctx *ctx, bool ce, int O, int N, const char *pat, const float *tg, int ldt, const float *Y, int ldy, float *d_error)
+{
+    if (ldt < O || ldy < O) return fail(ctx, "post-output error: leading dimension too small");
+    const size_t total = (size_t)N * O;
+    int blocks = ew_blocks(ctx, total, 256); if (blocks > 1024) blocks = 1024;
+    BL_CHECK(ensure_scratch(ctx, (size_t)blocks * sizeof(float)));
+    TimedRegion timed(ctx, 3);
+    if (ce) dense_error_kernel<true><<<blocks, 256, 0, ctx->stream>>>(O, total, pat, tg, ldt, Y, ldy, ctx->scratch);
+    else    dense_error_kernel<false><<<blocks, 256, 0, ctx->stream>>>(O, total, pat, tg, ldt, Y, ldy, ctx->scratch);
+    BL_LAUNCHED(ctx);
+    dense_error_finish_kernel<<<1, 32, 0, ctx->stream>>>(blocks, ce ? 1.0f : 0.5f, ctx->scratch, d_error);
+    BL_LAUNCHED(ctx);
+    return 0;
+}
+
+static int dense_backward(bl_ctx *ctx, bool ce, int O, int N, const char *pat, const float *tg, int ldt, const float *Y, int ldy, float *dY, int lddy)
+{
+    if (ldt < O || ldy < O || lddy < O) return fail(ctx, "post-output backward: leading dimension too small");
+    const size_t total = (size_t)N * O;
+    const int blocks = ew_blocks(ctx, total, 256);
+    TimedRegion timed(ctx, 3);
+    if (ce) dense_bwd_kernel<true><<<blocks, 256, 0, ctx->stream>>>(O, total, pat, tg, ldt, Y, ldy, dY, lddy);
+    else    dense_bwd_kernel<false><<<blocks, 256, 0, ctx->stream>>>(O, total, pat, tg, ldt, Y, ldy, dY, lddy);
+    BL_LAUNCHED(ctx);
+    return 0;
+}
+
+int bl_ce_error(bl_ctx *ctx, int O, int N, const char *p, const float *t, int ldt, const float *Y, int ldy, float *e) { return dense_error(ctx, true, O, N, p, t, ldt, Y, ldy, e); }
+int bl_sse_error(bl_ctx *ctx, int O, int N, const char *p, const float *t, int ldt, const float *Y, int ldy, float *e) { return dense_error(ctx, false, O, N, p, t, ldt, Y, ldy, e); }
+int bl_ce_backward(bl_ctx *ctx, int O, int N, const char *p, const float *t, int ldt, const float *Y, int ldy, float *dY, int lddy) { return dense_backward(ctx, true, O, N, p, t, ldt, Y, ldy, dY, lddy); }
+int bl_sse_backward(bl_ctx *ctx, int O, int N, const char *p, const float *t, int ldt, const float *Y, int ldy, float *dY, int lddy) { return dense_backward(ctx, false, O, N, p, t, ldt, Y, ldy, dY, lddy); }
+
+int bl_sgd_update(bl_ctx *ctx, size_t n, float lr, float mom, float *W, const float *dW, float *deltas)
+{
+    if (!n) return 0;
+    TimedRegion timed(ctx, 3);
+    sgd_kernel<<<ew_blocks(ctx, n, 256), 256, 0, ctx->stream>>>(n, lr, mom, W, dW, deltas);
+    BL_LAUNCHED(ctx);
+    return 0;
+}
+
+int bl_vector_add(bl_ctx *ctx, size_t n, const float *x, float *y)
+{
+    if (!n) return 0;
+    TimedRegion timed(ctx, 3);
+    vector_add_kernel<<<ew_blocks(ctx, n, 256), 256, 0, ctx->stream>>>(n, x, y);
+    BL_LAUNCHED(ctx);
+    return 0;
+}
+
+} // extern "C"

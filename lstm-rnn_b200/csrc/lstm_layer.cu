@@ -1,0 +1,258 @@
+// LSTM / BLSTM layer passes behind the C ABI (bl_lstm_*): orchestration of the projection GEMM, the persistent
+// recurrent kernels and the gradient contractions.  Reference: layers/LstmLayer.cu:763-886 (forward), :888-1051 (backward).
+//
+// HBM layout owned by the plan (all fp32):
+//   acts   [maxT*S][4L]  column g*L + d*H + j : projection output, overwritten in place by the activated gates
+//                         (the reference keeps 8 separate [N][H] arrays; one [N][4L] matrix lets ONE GEMM with
+//                          M = 4L produce all gates of both directions straight from the unmodified weight vector,
+//                          whose input block is exactly the [P x 4L] column-major matrix of these columns)
+//   deltas [maxT*S][4L]  same columns: the clipped gate deltas
+//   cst    [maxT*S][L]   cell states, column d*H + j;  cerr [maxT*S][L] cell-state errors
+//   hx / dx              L2-resident step-parity exchange buffers of the persistent kernels
+// The layer output Y [N][L] is written directly by the recurrent kernel (no ResortOutputsFn pass, :140-161),
+// and the output errors dY [N][L] are read directly (no ResortOutputErrorsFn pass, :163-188).
+#include "lstm_recurrent.cuh"
+#include <cstdlib>
+
+namespace bl {
+int gemm_f32_simt(bl_ctx *ctx, int transA, int transB, int m, int n, int k,
+                  const float *A, int lda, const float *B, int ldb, float *C, int ldc, int accumulate);
+}
+
+struct bl_lstm_plan {
+    bl_ctx *ctx;
+    int P, L, H, ndir, S, maxT;
+    float bias;
+    bl::RecGeom gf, gb;
+    float *acts, *deltas, *cst, *cerr, *hx, *dx, *gpart;
+    unsigned *flags_f, *flags_b;
+    int gsplit;
+    int lastT;
+};
+
+namespace bl {
+
+// Bias and peephole gradients (the non-GEMM part of ComputeWeightUpdateFn, LstmLayer.cu:392-408, 440-475).
+// grid (ceil(L/32), nsplit), block (32, 8): column = d*H + j of the layer, rows = a slice of the patterns.
+// part[split][7][L]: 4 bias sums (bias*delta), IG / FG peephole (time-shifted cell state), OG peephole (unshifted).
+__global__ void lstm_small_grads_kernel(int N, int S, int H, int L, float bias, const float *__restrict__ deltas,
+                                        const float *__restrict__ cst, float *__restrict__ part, int rows_per_split)
+{
+    __shared__ float red[8][7][33];
+    const int col = blockIdx.x * 32 + threadIdx.x;
+    const int n0 = blockIdx.y * rows_per_split, n1 = min(N, n0 + rows_per_split);
+    float acc[7] = {0, 0, 0, 0, 0, 0, 0};
+    if (col < L) {
+        const int d = col / H;
+        for (int n = n0 + threadIdx.y; n < n1; n += 8) {
+            const float *dp = deltas + (size_t)n * 4 * L + col;
+            const float dni = dp[0], dig = dp[L], dfg = dp[2 * L], dog = dp[3 * L];
+            acc[0] += bias * dni; acc[1] += bias * dig; acc[2] += bias * dfg; acc[3] += bias * dog;
+            acc[6] += cst[(size_t)n * L + col] * dog;                               // OG: no time shift (:456-458)
+            // IG/FG: fw pairs delta[n] with c[n-S] for n >= S; bw pairs delta[n] with c[n+S] for n < N-S (:460-468, 493-500)
+            const int ns = (d == 0) ? n - S : n + S;
+            if (ns >= 0 && ns < N) {
+                const float cs = cst[(size_t)ns * L + col];
+                acc[4] += cs * dig; acc[5] += cs * dfg;
+            }
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 7; ++i) red[threadIdx.y][i][threadIdx.x] = acc[i];
+    __syncthreads();
+    if (threadIdx.y == 0 && col < L) {
+#pragma unroll
+        for (int i = 0; i < 7; ++i) {
+            float s = 0.0f;
+            for (int y = 0; y < 8; ++y) s += red[y][i][threadIdx.x];
+            part[((size_t)blockIdx.y * 7 + i) * L + col] = s;
+        }
+    }
+}
+
+__global__ void lstm_small_grads_finish_kernel(int L, int nsplit, const float *__restrict__ part,
+                                               float *__restrict__ dWbias, float *__restrict__ dWpeep)
+{
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= 7 * L) return;
+    const int i = idx / L, col = idx % L;
+    float s = 0.0f;
+    for (int z = 0; z < nsplit; ++z) s += part[((size_t)z * 7 + i) * L + col];
+    if (i < 4) dWbias[i * L + col] = s;          // bias block: g*L + d*H + j
+    else       dWpeep[(i - 4) * L + col] = s;    // peephole block: q*L + d*H + j
+}
+
+__global__ void gather_cols_kernel(int N, int H, const float *__restrict__ src, int ld, int col0, float *__restrict__ dst)
+{
+    const size_t total = (size_t)N * H;
+    for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x)
+        dst[e] = src[(e / H) * ld + col0 + (e % H)];
+}
+
+} // namespace bl
+
+extern "C" {
+
+size_t bl_lstm_num_weights(int P, int L, int bidirectional)
+{
+    return (size_t)L * (4 * ((size_t)P + 1) + (bidirectional ? 2 : 4) * (size_t)L + 3);
+}
+
+int bl_lstm_plan_create(bl_ctx *ctx, int P, int L, int bidirectional, int S, int maxT, float bias, bl_lstm_plan **out)
+{
+    if (!ctx) return bl::fail(nullptr, "bl_lstm_plan_create: ctx is NULL");
+    if (!out) return bl::fail(ctx, "bl_lstm_plan_create: out is NULL");
+    *out = nullptr;
+    if (P <= 0 || L <= 0 || S <= 0 || maxT <= 0) return bl::fail(ctx, "bl_lstm_plan_create: bad sizes P=%d L=%d S=%d maxT=%d", P, L, S, maxT);
+    if (bidirectional && (L % 2)) return bl::fail(ctx, "Cannot create a bidirectional layer with an odd layer size");   // LstmLayer.cu:528-529
+    bl_lstm_plan *pl = new bl_lstm_plan();
+    pl->ctx = ctx; pl->P = P; pl->L = L; pl->ndir = bidirectional ? 2 : 1; pl->H = L / pl->ndir;
+    pl->S = S; pl->maxT = maxT; pl->bias = bias; pl->lastT = 0;
+    pl->acts = pl->deltas = pl->cst = pl->cerr = pl->hx = pl->dx = pl->gpart = nullptr;
+    pl->flags_f = pl->flags_b = nullptr;
+
+    const int cap = ctx->smem_optin - 1024;
+    const char *ef = getenv("BLSTM_FWD_G"), *eb = getenv("BLSTM_BWD_G");
+    if (!bl::choose_geometry(false, pl->H, S, pl->ndir, ctx->num_sms, cap, ef ? atoi(ef) : 0, &pl->gf) ||
+        !bl::choose_geometry(true, pl->H, S, pl->ndir, ctx->num_sms, cap, eb ? atoi(eb) : 0, &pl->gb)) {
+        delete pl;
+        return bl::fail(ctx, "bl_lstm_plan_create: no persistent-kernel geometry fits (H=%d S=%d): recurrent weights do not fit in shared memory",
+                        L / (bidirectional ? 2 : 1), S);
+    }
+    const size_t N = (size_t)maxT * S;
+    const size_t hx_elems = (size_t)pl->ndir * 2 * S * pl->gf.RS, dx_elems = (size_t)pl->ndir * 2 * S * pl->gb.RS;
+    pl->gsplit = 64;
+    int rc = 0;
+    rc |= bl_malloc(ctx, (void **)&pl->acts, N * 4 * L * sizeof(float));
+    rc |= bl_malloc(ctx, (void **)&pl->deltas, N * 4 * L * sizeof(float));
+    rc |= bl_malloc(ctx, (void **)&pl->cst, N * L * sizeof(float));
+    rc |= bl_malloc(ctx, (void **)&pl->cerr, N * L * sizeof(float));
+    rc |= bl_malloc(ctx, (void **)&pl->hx, hx_elems * sizeof(float));
+    rc |= bl_malloc(ctx, (void **)&pl->dx, dx_elems * sizeof(float));
+    rc |= bl_malloc(ctx, (void **)&pl->gpart, (size_t)pl->gsplit * 7 * L * sizeof(float));
+    rc |= bl_malloc(ctx, (void **)&pl->flags_f, (size_t)pl->ndir * pl->gf.G * 32 * sizeof(unsigned));
+    rc |= bl_malloc(ctx, (void **)&pl->flags_b, (size_t)pl->ndir * pl->gb.G * 32 * sizeof(unsigned));
+    if (rc) { bl_lstm_plan_destroy(pl); return 1; }
+    // zero-filled like the reference's buffers (LstmLayer.cu:554); the exchange buffers' padding columns must stay zero
+    rc |= bl_memset(ctx, pl->acts, 0, N * 4 * L * sizeof(float));
+    rc |= bl_memset(ctx, pl->deltas, 0, N * 4 * L * sizeof(float));
+    rc |= bl_memset(ctx, pl->cst, 0, N * L * sizeof(float));
+    rc |= bl_memset(ctx, pl->cerr, 0, N * L * sizeof(float));
+    rc |= bl_memset(ctx, pl->hx, 0, hx_elems * sizeof(float));
+    rc |= bl_memset(ctx, pl->dx, 0, dx_elems * sizeof(float));
+    if (rc) { bl_lstm_plan_destroy(pl); return 1; }
+    *out = pl;
+    return 0;
+}
+
+void bl_lstm_plan_destroy(bl_lstm_plan *pl)
+{
+    if (!pl) return;
+    cudaStreamSynchronize(pl->ctx->stream);
+    void *bufs[] = { pl->acts, pl->deltas, pl->cst, pl->cerr, pl->hx, pl->dx, pl->gpart, pl->flags_f, pl->flags_b };
+    for (void *b : bufs) if (b) cudaFree(b);
+    delete pl;
+}
+
+int bl_lstm_plan_info(const bl_lstm_plan *pl, int *o)
+{
+    o[0] = pl->gf.G; o[1] = pl->gf.C; o[2] = pl->gf.CL; o[3] = (int)pl->gf.smem;
+    o[4] = pl->gb.G; o[5] = pl->gb.C; o[6] = pl->gb.CL; o[7] = (int)pl->gb.smem;
+    return 0;
+}
+
+int bl_lstm_forward(bl_lstm_plan *pl, const float *W, const float *X, int ldx, const char *patTypes,
+                    int T, int Tmin, float *Y, int ldy)
+{
+    bl_ctx *ctx = pl->ctx;
+    if (T <= 0 || T > pl->maxT) return bl::fail(ctx, "bl_lstm_forward: T=%d outside (0, maxT=%d]", T, pl->maxT);
+    if (ldx < pl->P || ldy < pl->L) return bl::fail(ctx, "bl_lstm_forward: leading dimension too small");
+    const int P = pl->P, L = pl->L, H = pl->H, S = pl->S, N = T * S;
+    // (1) input projection of all timesteps, all 4 gates, both directions: acts[4L x N] = Win^T[4L x P] * X[P x N]
+    //     (the 8 assignProduct calls of LstmLayer.cu:774-784 as one GEMM; Win is the weight vector's first 4LP floats)
+    BL_CHECK(bl_gemm_f32(ctx, 1, 0, 4 * L, N, P, W, P, X, ldx, pl->acts, 4 * L, 0, ctx->gemm_mode));
+    // (2) recurrent sweep, both directions concurrently
+    bl::RecFwdParams p;
+    p.Wb = W + (size_t)4 * L * P; p.Wi = p.Wb + 4 * L; p.Wp = p.Wi + (size_t)4 * L * H;
+    p.acts = pl->acts; p.cst = pl->cst; p.Y = Y; p.ldy = ldy; p.hx = pl->hx; p.flags = pl->flags_f; p.pat = patTypes;
+    p.T = T; p.Tmin = Tmin; p.S = S; p.H = H; p.L = L; p.ndir = pl->ndir; p.bias = pl->bias; p.g = pl->gf;
+    BL_CHECK(bl::launch_lstm_fwd(ctx, p));
+    pl->lastT = T;
+    return 0;
+}
+
+int bl_lstm_backward(bl_lstm_plan *pl, const float *W, const float *X, int ldx, const float *Y, int ldy,
+                     float *dY, int lddy, const char *patTypes, int T, int Tmin,
+                     float *dX, int lddx, float *dW)
+{
+    bl_ctx *ctx = pl->ctx;
+    if (T <= 0 || T > pl->maxT) return bl::fail(ctx, "bl_lstm_backward: T=%d outside (0, maxT=%d]", T, pl->maxT);
+    if (T != pl->lastT) return bl::fail(ctx, "bl_lstm_backward: must follow bl_lstm_forward on the same fraction (T=%d, forward saw %d)", T, pl->lastT);
+    if (ldx < pl->P || ldy < pl->L || lddy < pl->L || (dX && lddx < pl->P)) return bl::fail(ctx, "bl_lstm_backward: leading dimension too small");
+    const int P = pl->P, L = pl->L, H = pl->H, S = pl->S, N = T * S;
+    const size_t inW = (size_t)L * P;
+    float *dWbias = dW + 4 * inW, *dWint = dWbias + 4 * L, *dWpeep = dWint + (size_t)4 * L * H;
+
+    // (1) BPTT sweep
+    bl::RecBwdParams p;
+    p.Wi = W + 4 * inW + 4 * L; p.Wp = p.Wi + (size_t)4 * L * H;
+    p.acts = pl->acts; p.cst = pl->cst; p.deltas = pl->deltas; p.cerr = pl->cerr; p.dY = dY; p.lddy = lddy;
+    p.dx = pl->dx; p.flags = pl->flags_b; p.pat = patTypes;
+    p.T = T; p.Tmin = Tmin; p.S = S; p.H = H; p.L = L; p.ndir = pl->ndir; p.g = pl->gb;
+    BL_CHECK(bl::launch_lstm_bwd(ctx, p));
+
+    // (2) error to the preceding layer: dX[P x N] = Win[P x 4L] * deltas[4L x N]   (the 8 products of :996-1006)
+    if (dX) BL_CHECK(bl_gemm_f32(ctx, 0, 0, P, N, 4 * L, W, P, pl->deltas, 4 * L, dX, lddx, 0, ctx->gemm_mode));
+
+    // (3) input weight gradients: dWin[P x 4L] = X[P x N] * deltas^T   (ComputeWeightUpdateFn case 0x0, :372-389)
+    BL_CHECK(bl_gemm_f32(ctx, 0, 1, P, 4 * L, N, X, ldx, pl->deltas, 4 * L, dW, P, 0, ctx->gemm_mode));
+
+    // (4) recurrent weight gradients, one [H x H] block per (gate, direction) (case 0x8, :411-437, 493-500):
+    //     fw: dW[k,j] = sum_{n>=S}  h[n-S,k] * delta[n,j];   bw: dW[k,j] = sum_{n<N-S} h[n+S,k] * delta[n,j]
+    for (int g = 0; g < 4; ++g)
+        for (int d = 0; d < pl->ndir; ++d) {
+            float *blk = dWint + (size_t)g * L * H + (size_t)d * H * H;
+            const int col = g * L + d * H;
+            if (N - S > 0) {
+                const float *A = (d == 0) ? Y : Y + (size_t)S * ldy + H;
+                const float *B = (d == 0) ? pl->deltas + (size_t)S * 4 * L + col : pl->deltas + col;
+                BL_CHECK(bl_gemm_f32(ctx, 0, 1, H, H, N - S, A, ldy, B, 4 * L, blk, H, 0, ctx->gemm_mode));
+            } else {
+                BL_CHECK(bl_memset(ctx, blk, 0, (size_t)H * H * sizeof(float)));
+            }
+        }
+
+    // (5) bias + peephole gradients
+    {
+        bl::TimedRegion timed(ctx, 3);
+        int nsplit = pl->gsplit;
+        int rows = bl::cdiv(N, nsplit);
+        if (rows < 64) rows = 64;
+        nsplit = bl::cdiv(N, rows);
+        dim3 grid(bl::cdiv(L, 32), nsplit), block(32, 8);
+        bl::lstm_small_grads_kernel<<<grid, block, 0, ctx->stream>>>(N, S, H, L, pl->bias, pl->deltas, pl->cst, pl->gpart, rows);
+        BL_LAUNCHED(ctx);
+        bl::lstm_small_grads_finish_kernel<<<bl::cdiv(7 * L, 256), 256, 0, ctx->stream>>>(L, nsplit, pl->gpart, dWbias, dWpeep);
+        BL_LAUNCHED(ctx);
+    }
+    return 0;
+}
+
+int bl_lstm_get_internal(bl_lstm_plan *pl, int dir, int which, int T, float *dst)
+{
+    bl_ctx *ctx = pl->ctx;
+    if (dir < 0 || dir >= pl->ndir || which < 0 || which > 9 || T <= 0 || T > pl->maxT)
+        return bl::fail(ctx, "bl_lstm_get_internal: bad selector");
+    const int L = pl->L, H = pl->H, N = T * pl->S;
+    const float *src; int ld, col0;
+    if (which == 0)      { src = pl->cst;    ld = L;     col0 = dir * H; }
+    else if (which == 1) { src = pl->cerr;   ld = L;     col0 = dir * H; }
+    else if (which < 6)  { src = pl->acts;   ld = 4 * L; col0 = (which - 2) * L + dir * H; }
+    else                 { src = pl->deltas; ld = 4 * L; col0 = (which - 6) * L + dir * H; }
+    int blocks = (int)bl::cdivz((size_t)N * H, 256); if (blocks > 4096) blocks = 4096;
+    bl::gather_cols_kernel<<<blocks, 256, 0, ctx->stream>>>(N, H, src, ld, col0, dst);
+    BL_LAUNCHED(ctx);
+    return 0;
+}
+
+} // extern "C"

@@ -1,0 +1,59 @@
+// Persistent recurrent kernels of the LSTM layer: geometry + launch interface (lstm_recurrent.cu).
+#pragma once
+#include "common.cuh"
+
+namespace bl {
+
+constexpr int REC_NT = 512;            // threads per CTA (16 warps, 1 CTA per SM)
+constexpr int REC_NW = REC_NT / 32;
+constexpr int REC_NPAIR = 2;           // (cell, sequence) pairs per thread in the elementwise phase
+
+// Launch geometry of one persistent kernel.  One CTA owns CL cells of one direction for the SG sequences of
+// one sequence group; its slice of the recurrent weights stays in shared memory for the whole pass.
+struct RecGeom {
+    int G, C, CL, SG;       // sequence groups, cell slices per (direction, group), cells per CTA, sequences per group
+    int R;                  // GEMM rows per CTA: 4*CL (forward: gate x cell), CL (BPTT: cell)
+    int LR, LS, LSlog;      // lanes along row quads / sequence quads (LR*LS == 32)
+    int WR, WS, KS;         // warp tiles along rows / sequences, K splits
+    int RQt, SQt;           // padded row quads / sequence quads (WR*LR, WS*LS)
+    int Rpad, Spad;         // 4*RQt, 4*SQt
+    int K4, KB4;            // contraction length and per-split length in float4 units
+    int RS;                 // shared-memory row stride (floats) of both operand tiles, == global exchange row stride
+    int RP;                 // row pitch of the staging buffer
+    int Hpad;
+    size_t smem;
+    double cost;
+};
+
+bool choose_geometry(bool bwd, int H, int S, int ndir, int num_sms, int smem_cap, int forceG, RecGeom *out);
+
+struct RecFwdParams {
+    const float *Wb, *Wi, *Wp;      // bias / internal / peephole segments of the layer's weight vector
+    float *acts;                    // [N][4L]  pre-activations in, activations out (column g*L + d*H + j)
+    float *cst;                     // [N][L]   cell states
+    float *Y; int ldy;              // [N][ldy] layer outputs
+    float *hx;                      // [ndir][2][S][Hpad] step-parity exchange buffer for h
+    unsigned *flags;                // [ndir*G*32] step counters
+    const char *pat;
+    int T, Tmin, S, H, L, ndir;
+    float bias;
+    RecGeom g;
+};
+
+struct RecBwdParams {
+    const float *Wi, *Wp;
+    const float *acts, *cst;        // from the forward pass
+    float *deltas;                  // [N][4L]
+    float *cerr;                    // [N][L] cell state errors
+    float *dY; int lddy;            // [N][lddy] output errors (updated in place when !bidirectional)
+    float *dx;                      // [ndir][2][S][RS] step-parity exchange buffer for the 4 gate deltas
+    unsigned *flags;
+    const char *pat;
+    int T, Tmin, S, H, L, ndir;
+    RecGeom g;
+};
+
+int launch_lstm_fwd(bl_ctx *ctx, const RecFwdParams &p);
+int launch_lstm_bwd(bl_ctx *ctx, const RecBwdParams &p);
+
+} // namespace bl

@@ -1,0 +1,137 @@
+#include "DataSet.hpp"
+#include <algorithm>
+#include <cstring>
+#include <limits>
+#include <stdexcept>
+
+namespace data_sets {
+
+DataSetFraction *DataSetFraction::fromPacked(bl_ctx *ctx, int S, int T, int Tmin, int numSeqs, const int *seqLengths, int P, int O,
+                                             const real_t *inputs, const char *patTypes, const int *targetClasses, const real_t *targets)
+{
+    DataSetFraction *f = new DataSetFraction;
+    f->m_inputPatternSize = P; f->m_outputPatternSize = O; f->m_maxSeqLength = T; f->m_minSeqLength = Tmin; f->m_parallelSequences = S;
+    for (int i = 0; i < numSeqs; ++i) {
+        seq_info_t si; si.originalSeqIdx = i; si.length = seqLengths ? seqLengths[i] : T; si.seqTag = "seq";
+        f->m_seqInfo.push_back(si);
+    }
+    const size_t n = (size_t)T * S;
+    f->m_inputs.resize(ctx, n * P, 0);
+    std::memcpy(f->m_inputs.data(), inputs, n * P * sizeof(real_t));
+    f->m_patTypes.resize(ctx, n, PATTYPE_NONE);
+    std::memcpy(f->m_patTypes.data(), patTypes, n);
+    if (targetClasses) { f->m_targetClasses.resize(ctx, n, -1); std::memcpy(f->m_targetClasses.data(), targetClasses, n * sizeof(int)); }
+    if (targets) { f->m_outputs.resize(ctx, n * O, 0); std::memcpy(f->m_outputs.data(), targets, n * O * sizeof(real_t)); }
+    return f;
+}
+
+static bool comp_seqs(const DataSet::sequence_t &a, const DataSet::sequence_t &b) { return a.length < b.length; }   // DataSet.cpp:165-168
+
+DataSet::DataSet(bl_ctx *ctx, int numSeqs, const int *seqLengths, int P, int O, const real_t *inputs, const int *targetClasses,
+                 const real_t *targets, int parSeq, int truncSeqLength, bool trainingMode, int rank, int world)
+    : m_ctx(ctx), m_isClassificationData(targetClasses != nullptr), m_parallelSequences(parSeq), m_rank(rank), m_world(world)
+    , m_totalSequences(0), m_totalTimesteps(0)
+    , m_minSeqLength(std::numeric_limits<int>::max()), m_maxSeqLength(std::numeric_limits<int>::min())
+    , m_inputPatternSize(P), m_outputPatternSize(O), m_curFirstSeqIdx(-1)
+{
+    if ((targetClasses == nullptr) == (targets == nullptr))
+        throw std::runtime_error("DataSet needs exactly one of target classes / target patterns");
+    if (parSeq < 1 || world < 1 || rank < 0 || rank >= world)
+        throw std::runtime_error("DataSet: bad parallel_sequences / rank / world");
+    size_t begin = 0;
+    for (int i = 0; i < numSeqs; ++i) {
+        int seqLength = seqLengths[i];
+        m_totalTimesteps += seqLength;                                            // DataSet.cpp:523 (original frames)
+        int k = 0;
+        while (seqLength > 0) {                                                   // DataSet.cpp:527-542
+            sequence_t seq;
+            seq.originalSeqIdx = k;
+            if (truncSeqLength > 0 && seqLength > 1.5 * truncSeqLength)
+                seq.length = std::min(truncSeqLength, seqLength);
+            else
+                seq.length = seqLength;
+            seq.seqTag = "seq" + std::to_string(i);
+            seq.inputsBegin = begin; seq.targetsBegin = begin;
+            m_sequences.push_back(seq);
+            begin += (size_t)seq.length;
+            seqLength -= seq.length;
+            ++k;
+        }
+    }
+    for (const sequence_t &s : m_sequences) {
+        m_minSeqLength = std::min(m_minSeqLength, s.length);
+        m_maxSeqLength = std::max(m_maxSeqLength, s.length);
+    }
+    m_inputs.assign(inputs, inputs + begin * P);
+    if (targetClasses) m_targetClasses.assign(targetClasses, targetClasses + begin);
+    else m_targets.assign(targets, targets + begin * O);
+    m_totalSequences = (int)m_sequences.size();                                   // DataSet.cpp:602 (chunks)
+    if (trainingMode)
+        std::sort(m_sequences.begin(), m_sequences.end(), comp_seqs);             // DataSet.cpp:603-605
+}
+
+int DataSet::numFractions() const
+{
+    const int gs = m_parallelSequences * m_world;
+    return ((int)m_sequences.size() + gs - 1) / gs;
+}
+
+std::shared_ptr<DataSetFraction> DataSet::makeFraction(int firstSeqIdx) const
+{
+    const int S = m_parallelSequences, P = m_inputPatternSize, O = m_outputPatternSize;
+    std::shared_ptr<DataSetFraction> frac(new DataSetFraction);
+    frac->m_inputPatternSize = P;
+    frac->m_outputPatternSize = O;
+    frac->m_parallelSequences = S;
+    frac->m_maxSeqLength = std::numeric_limits<int>::min();
+    frac->m_minSeqLength = std::numeric_limits<int>::max();
+    const int first = firstSeqIdx + m_rank * S;
+    for (int seqIdx = first; seqIdx < first + S; ++seqIdx) {
+        if (seqIdx < (int)m_sequences.size()) {
+            frac->m_maxSeqLength = std::max(frac->m_maxSeqLength, m_sequences[seqIdx].length);
+            frac->m_minSeqLength = std::min(frac->m_minSeqLength, m_sequences[seqIdx].length);
+            DataSetFraction::seq_info_t si;
+            si.originalSeqIdx = m_sequences[seqIdx].originalSeqIdx;
+            si.length = m_sequences[seqIdx].length;
+            si.seqTag = m_sequences[seqIdx].seqTag;
+            frac->m_seqInfo.push_back(si);
+        }
+    }
+    if (frac->m_seqInfo.empty()) { frac->m_maxSeqLength = 0; frac->m_minSeqLength = 0; return frac; }   // empty shard
+
+    const size_t slots = (size_t)frac->m_maxSeqLength * S;
+    frac->m_inputs.resize(m_ctx, slots * P, 0);
+    frac->m_patTypes.resize(m_ctx, slots, PATTYPE_NONE);
+    if (m_isClassificationData) frac->m_targetClasses.resize(m_ctx, slots, -1);
+    else frac->m_outputs.resize(m_ctx, slots * O, 0);
+
+    for (int i = 0; i < S; ++i) {
+        if (first + i >= (int)m_sequences.size()) continue;
+        const sequence_t &seq = m_sequences[first + i];
+        for (int t = 0; t < seq.length; ++t) {
+            const size_t slot = (size_t)t * S + i;                                // DataSet.cpp:358
+            std::memcpy(frac->m_inputs.data() + slot * P, m_inputs.data() + (seq.inputsBegin + t) * P, sizeof(real_t) * P);
+            if (m_isClassificationData)
+                frac->m_targetClasses[slot] = m_targetClasses[seq.targetsBegin + t];
+            else
+                std::memcpy(frac->m_outputs.data() + slot * O, m_targets.data() + (seq.targetsBegin + t) * O, sizeof(real_t) * O);
+            frac->m_patTypes[slot] = (t == 0) ? PATTYPE_FIRST : (t == seq.length - 1) ? PATTYPE_LAST : PATTYPE_NORMAL;   // :397-406
+        }
+    }
+    return frac;
+}
+
+std::shared_ptr<DataSetFraction> DataSet::getNextFraction()
+{
+    if (m_curFirstSeqIdx == -1) m_curFirstSeqIdx = 0;
+    std::shared_ptr<DataSetFraction> frac;
+    if (m_curFirstSeqIdx < (int)m_sequences.size()) {
+        frac = makeFraction(m_curFirstSeqIdx);
+        m_curFirstSeqIdx += m_parallelSequences * m_world;
+    } else {
+        m_curFirstSeqIdx = 0;                                                     // DataSet.cpp:662-664
+    }
+    return frac;
+}
+
+} // namespace data_sets

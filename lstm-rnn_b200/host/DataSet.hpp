@@ -1,0 +1,56 @@
+// In-memory data set + fraction builder with the reference's semantics (data_sets/DataSet.cpp:300-414 packing,
+// :527-542 --truncate_seq chunking, :603-605 sort by length in training mode, :632-668 fraction iteration) and the
+// data-parallel extension: rank r of W takes columns [r*S, (r+1)*S) of each global fraction of W*S sequences.
+// The NetCDF front end (DataSet.cpp:44-144, 443-606) lives in NetCdf.hpp; it only fills the arrays handed in here.
+#pragma once
+#include <memory>
+#include <string>
+#include <vector>
+#include "DataSetFraction.hpp"
+
+namespace data_sets {
+
+class DataSet {
+public:
+    struct sequence_t {
+        int         originalSeqIdx;
+        int         length;
+        std::string seqTag;
+        size_t      inputsBegin;      // offsets in patterns into the frame arrays
+        size_t      targetsBegin;
+    };
+
+    // frames: inputs [totalFrames][P]; exactly one of targetClasses [totalFrames] / targets [totalFrames][O].
+    // parSeq = parallel sequences PER RANK; truncSeqLength = --truncate_seq; trainingMode sorts by length.
+    DataSet(bl_ctx *ctx, int numSeqs, const int *seqLengths, int P, int O, const real_t *inputs, const int *targetClasses,
+            const real_t *targets, int parSeq, int truncSeqLength = 0, bool trainingMode = true, int rank = 0, int world = 1);
+
+    bool isClassificationData() const { return m_isClassificationData; }
+    bool empty() const { return m_totalTimesteps == 0; }
+    int totalSequences() const { return m_totalSequences; }
+    int totalTimesteps() const { return m_totalTimesteps; }
+    int minSeqLength() const { return m_minSeqLength; }
+    int maxSeqLength() const { return m_maxSeqLength; }
+    int inputPatternSize() const { return m_inputPatternSize; }
+    int outputPatternSize() const { return m_outputPatternSize; }
+    int numFractions() const;
+    const std::vector<sequence_t> &sequences() const { return m_sequences; }
+
+    // next fraction of the epoch, or null once at the end of each epoch (then the iteration restarts).
+    // With world > 1 a rank whose shard is empty gets a fraction with numSequences() == 0 and maxSeqLength() == 0.
+    std::shared_ptr<DataSetFraction> getNextFraction();
+    // fraction starting at global sequence index firstSeqIdx (this rank's shard of it)
+    std::shared_ptr<DataSetFraction> makeFraction(int firstSeqIdx) const;
+
+private:
+    bl_ctx *m_ctx;
+    bool m_isClassificationData;
+    int m_parallelSequences, m_rank, m_world;
+    int m_totalSequences, m_totalTimesteps, m_minSeqLength, m_maxSeqLength, m_inputPatternSize, m_outputPatternSize;
+    std::vector<real_t> m_inputs, m_targets;
+    std::vector<int> m_targetClasses;
+    std::vector<sequence_t> m_sequences;
+    int m_curFirstSeqIdx;
+};
+
+} // namespace data_sets

@@ -66,5 +66,5 @@ done
 pids+=($!)
 for p in "${pids[@]}"; do wait "$p"; done
 
-"$NVCC" -shared -arch=sm_100a -o "$LIB" "$WORK"/obj/*.o -lcublas
+"$NVCC" -shared -Xlinker -Bsymbolic -arch=sm_100a -o "$LIB" "$WORK"/obj/*.o -lcublas
 echo "[build_ref] built $LIB"

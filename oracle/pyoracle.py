@@ -312,7 +312,7 @@ def ref_available():
 def ref_lib():
     global _ref
     if _ref is None:
-        L = ctypes.CDLL(REF_SO)
+        L = ctypes.CDLL(REF_SO, mode=ctypes.RTLD_LOCAL)
         vp, ci, cl = ctypes.c_void_p, ctypes.c_int, ctypes.c_long
         L.cref_last_error.restype = ctypes.c_char_p
         L.cref_net_create.restype = vp

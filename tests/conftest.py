@@ -19,3 +19,12 @@ def oracle():
     from oracle import pyoracle
     pyoracle.build(ref=os.path.isdir("/root/reference"))
     return pyoracle
+
+
+@pytest.fixture(scope="session")
+def gpu_ctx():
+    """One bl_ctx on cuda:0 for the GPU parity tests; the product path has no CPU fallback, so this fails loudly without a device."""
+    import currennt_b200 as cb
+    ctx = cb.Context(0)
+    yield ctx
+    ctx.close()

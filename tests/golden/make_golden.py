@@ -1,0 +1,69 @@
+"""Generates tests/golden/*.npz from the REFERENCE ITSELF: the unmodified CURRENNT CPU objects compiled by
+oracle/build_ref.sh from /root/reference (oracle/_ref/libcurrennt_ref.so).  Run in the build container:
+
+    python tests/golden/make_golden.py
+
+Each file holds the network JSON, the per-layer initial weights, one packed fraction, and what the reference
+computed for it: every layer's outputs / outputErrors / weightUpdates, the objective and (multiclass) the number of
+correct classifications.  tests/test_golden.py replays them against the C restatement (CPU) and the CUDA path (GPU).
+"""
+import json
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path[:0] = [ROOT, os.path.join(ROOT, "tests"), os.path.join(ROOT, "lstm-rnn_b200", "python")]
+
+import synth                      # noqa: E402
+from helpers import small_case   # noqa: E402
+from oracle import pyoracle      # noqa: E402
+
+CASES = {
+    # name: (network json, S, sequence lengths, classes, dense target size, seed)
+    "blstm_softmax_ragged": (synth.network_json(13, [12, 8], 7), 6, [3, 5, 5, 8, 9], 7, 0, 21),
+    "lstm_softmax": (synth.network_json(9, [("lstm", 10)], 5), 4, [2, 6, 6, 7], 5, 0, 22),
+    "test1_shape": (synth.config("C1")["net"], 10, [11, 12, 12, 13, 13, 14, 15, 15, 16, 17], 51, 0, 23),
+    "autoencoder_sse": (synth.network_json(8, [12, 16, 12], 8, "feedforward_identity", "sse"), 5, [4, 6, 7, 7], 0, 8, 24),
+    "softmax_ce": (synth.network_json(6, [10], 5, "softmax", "ce"), 3, [3, 4, 6], 0, 5, 25),
+    "mixed_ff": (synth.network_json(9, [("blstm", 8), ("feedforward_tanh", 5), ("lstm", 6), ("feedforward_logistic", 4), ("blstm", 10)], 6),
+                 5, [1, 4, 7, 7, 9], 6, 0, 26),
+}
+
+
+def main():
+    pyoracle.build(ref=True)
+    for name, (net_json, S, lengths, classes, tsize, seed) in CASES.items():
+        weights, frac = small_case(pyoracle, net_json, S, lengths, seed, classes=classes, target_size=tsize)
+        if name == "softmax_ce":
+            t = np.abs(frac.targets) + 0.1
+            frac.targets[:] = t / t.sum(1, keepdims=True)
+        ref = pyoracle.RefNet(net_json, S, max(lengths) + 3)
+        for i, w in enumerate(weights):
+            if len(w):
+                ref.set_weights(i, w)
+        ref.load_fraction(frac)
+        ref.forward()
+        out = {"net_json": np.array(net_json), "S": S, "T": frac.T, "Tmin": frac.Tmin, "seq_lengths": frac.seq_lengths,
+               "inputs": frac.inputs, "pat_types": frac.pat_types, "error": np.float32(ref.calculate_error())}
+        if frac.target_classes is not None:
+            out["target_classes"] = frac.target_classes
+            out["correct"] = ref.count_correct()
+        if frac.targets is not None:
+            out["targets"] = frac.targets
+        ref.backward()
+        layers = json.loads(net_json)["layers"]
+        for i, ly in enumerate(layers[:-1]):
+            out["w%d" % i] = weights[i]
+            out["outputs%d" % i] = ref.get_outputs(i)
+            if i:
+                out["output_errors%d" % i] = ref.get_output_errors(i)
+                out["weight_updates%d" % i] = ref.get_weight_updates(i)
+        np.savez_compressed(os.path.join(HERE, name + ".npz"), **out)
+        print(name, "N=%d" % frac.N, "error=%.6f" % out["error"])
+
+
+if __name__ == "__main__":
+    main()

@@ -34,3 +34,72 @@ def rel_err(a, b):
     d = float(np.max(np.abs(a - b))) if a.size else 0.0
     m = float(np.max(np.abs(b))) if b.size else 0.0
     return d / m if m > 0 else d
+
+
+class GoldenFraction:
+    """The packed fraction stored in a golden .npz, with the attribute names both checkers and the product binding use."""
+
+    def __init__(self, g):
+        import json
+        layers = json.loads(str(g["net_json"]))["layers"]
+        self.S, self.T, self.Tmin = int(g["S"]), int(g["T"]), int(g["Tmin"])
+        self.P, self.O = layers[0]["size"], layers[-1]["size"]
+        self.seq_lengths = np.ascontiguousarray(g["seq_lengths"], dtype=np.int32)
+        self.num_seqs = len(self.seq_lengths)
+        self.inputs = np.ascontiguousarray(g["inputs"], dtype=np.float32)
+        self.pat_types = np.ascontiguousarray(g["pat_types"], dtype=np.int8)
+        self.target_classes = np.ascontiguousarray(g["target_classes"], dtype=np.int32) if "target_classes" in g else None
+        self.targets = np.ascontiguousarray(g["targets"], dtype=np.float32) if "targets" in g else None
+        self.N = self.T * self.S
+
+
+def load_golden(name):
+    import os
+    return np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", name + ".npz"))
+
+
+GOLDEN = ["blstm_softmax_ragged", "lstm_softmax", "test1_shape", "autoencoder_sse", "softmax_ce", "mixed_ff"]
+
+
+def replay_golden(net_cls_factory, name):
+    """Runs a network object (oracle or product) on a golden case; returns (g, net)."""
+    import json
+    g = load_golden(name)
+    net_json = str(g["net_json"])
+    frac = GoldenFraction(g)
+    net = net_cls_factory(net_json, frac.S, frac.T + 3)
+    layers = json.loads(net_json)["layers"]
+    for i in range(len(layers) - 1):
+        w = g["w%d" % i]
+        if len(w):
+            net.set_weights(i, w)
+    net.load_fraction(frac)
+    net.forward()
+    err = net.calculate_error()
+    correct = net.count_correct() if "correct" in g else None
+    net.backward()
+    return g, net, layers, err, correct
+
+
+def compare_to_golden(g, net, layers, err, correct, tol, exact=False):
+    """tol applies to max|a-b|/max|b| per tensor (and to the objective relatively); exact demands bit equality."""
+    worst = {}
+    def cmp(key, a, b):
+        if exact:
+            assert np.array_equal(a, b), key
+        else:
+            r = rel_err(a, b)
+            worst[key] = r
+            assert r <= tol, (key, r)
+    if exact:
+        assert np.float32(err).tobytes() == np.float32(g["error"]).tobytes()
+    else:
+        assert abs(err - float(g["error"])) <= tol * abs(float(g["error"])) + 1e-12, (err, float(g["error"]))
+    if correct is not None:
+        assert correct == int(g["correct"])
+    for i in range(len(layers) - 1):
+        cmp("outputs%d" % i, net.get_outputs(i), g["outputs%d" % i])
+        if i:
+            cmp("output_errors%d" % i, net.get_output_errors(i), g["output_errors%d" % i])
+            cmp("weight_updates%d" % i, net.get_weight_updates(i), g["weight_updates%d" % i])
+    return worst

@@ -1,0 +1,219 @@
+"""GPU parity tests proper: the CUDA path, called through the C ABI, against the oracle on the same seeded inputs.
+Bar (BASELINE.json north_star): strict fp32 -> max|a-b|/max|b| <= 1e-5 per tensor on outputs and gradients;
+counts, packing and label indexing exact."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+import synth
+from helpers import rel_err, run_net, small_case
+
+pytestmark = pytest.mark.gpu
+
+STRICT_TOL = 1e-5
+
+
+# ----------------------------------------------------------------------------- GEMM (helpers::Matrix drop-in)
+GEMM_SHAPES = [
+    # transA, transB, m, n, k, pad
+    (1, 0, 40, 54, 13, 0), (1, 0, 2000, 300, 123, 1), (1, 0, 183, 257, 500, 0),
+    (0, 0, 123, 300, 2000, 0), (0, 0, 7, 5, 3, 2),
+    (0, 1, 500, 2000, 3000, 0), (0, 1, 250, 250, 2900, 3), (0, 1, 39, 51, 170, 1),
+    (1, 0, 129, 129, 17, 0), (0, 0, 128, 128, 16, 0),
+]
+
+
+@pytest.mark.parametrize("shape", GEMM_SHAPES, ids=lambda s: "x".join(map(str, s)))
+@pytest.mark.parametrize("accumulate", [0, 1])
+def test_gemm_matches_fp64(gpu_ctx, oracle, shape, accumulate):
+    tA, tB, m, n, k, pad = shape
+    rng = np.random.default_rng(m * 7 + n * 3 + k)
+    rowsA, colsA = (k, m) if tA else (m, k)
+    rowsB, colsB = (n, k) if tB else (k, n)
+    lda, ldb, ldc = rowsA + pad, rowsB + pad, m + pad
+    A = rng.standard_normal((colsA, lda)).astype(np.float32)      # column-major: column j at A[j, :rows]
+    B = rng.standard_normal((colsB, ldb)).astype(np.float32)
+    C0 = rng.standard_normal((n, ldc)).astype(np.float32)
+    dA, dB, dC = gpu_ctx.to_device(A), gpu_ctx.to_device(B), gpu_ctx.to_device(C0)
+    gpu_ctx.gemm(tA, tB, m, n, k, dA, lda, dB, ldb, dC, ldc, accumulate)
+    C = gpu_ctx.to_host(dC, (n, ldc))
+    for p in (dA, dB, dC):
+        gpu_ctx.free(p)
+    Am = A[:, :rowsA].T.astype(np.float64)                         # rowsA x colsA
+    Bm = B[:, :rowsB].T.astype(np.float64)
+    want = (Am.T if tA else Am) @ (Bm.T if tB else Bm)            # m x n
+    if accumulate:
+        want = want + C0[:, :m].T
+    assert rel_err(C[:, :m].T, want) <= 2e-6
+    if pad:
+        assert np.array_equal(C[:, m:], C0[:, m:])                 # padding rows of C untouched
+    # small shapes: also against the oracle's serial fp32 product (Matrix.cu semantics)
+    if m * n * k <= 200000 and not pad:
+        L = oracle.oracle_lib()
+        Co = np.ascontiguousarray(C0[:, :m]).copy()
+        Ao, Bo = np.ascontiguousarray(A[:, :rowsA]), np.ascontiguousarray(B[:, :rowsB])
+        assert L.orc_matrix_product(oracle._fp(Co), m, n, oracle._fp(Ao), rowsA, colsA, tA, oracle._fp(Bo), rowsB, colsB, tB, accumulate) == 0
+        assert rel_err(C[:, :m], Co) <= STRICT_TOL
+
+
+def test_gemm_rejects_tt(gpu_ctx):
+    d = gpu_ctx.to_device(np.zeros(16, np.float32))
+    with pytest.raises(RuntimeError, match="not implemented"):
+        gpu_ctx.gemm(1, 1, 2, 2, 2, d, 2, d, 2, d, 2)
+    gpu_ctx.free(d)
+
+
+# ----------------------------------------------------------------------------- whole networks against the oracle
+NET_CASES = [
+    # name, net, S, lengths, classes, dense target size
+    ("blstm_ragged", synth.network_json(7, [6], 5), 4, [3, 5, 5, 8], 5, 0),
+    ("blstm_short_last_fraction", synth.network_json(7, [6], 5), 4, [4, 6], 5, 0),
+    ("blstm_len1_sequence", synth.network_json(5, [4], 3), 3, [1, 1, 4], 3, 0),
+    ("lstm_uni", synth.network_json(5, [("lstm", 7)], 4), 3, [2, 6, 6], 4, 0),
+    ("lstm_uni_deep", synth.network_json(6, [("lstm", 9), ("lstm", 5)], 4), 5, [3, 3, 7, 9, 9], 4, 0),
+    ("deep_mixed", synth.network_json(9, [("blstm", 8), ("feedforward_tanh", 5), ("lstm", 6), ("feedforward_logistic", 4), ("blstm", 10)], 6),
+     5, [1, 4, 7, 7, 9], 6, 0),
+    ("sse_identity", synth.network_json(6, [8, 4], 6, "feedforward_identity", "sse"), 3, [5, 5, 7], 0, 6),
+    ("ce_softmax", synth.network_json(6, [8], 5, "softmax", "ce"), 3, [3, 4, 6], 0, 5),
+    ("equal_lengths", synth.network_json(4, [6], 3), 2, [5, 5], 3, 0),
+    ("odd_sizes_wide", synth.network_json(23, [62, 30], 19), 7, [9, 11, 14, 14, 15, 15, 16], 19, 0),
+    ("many_sequences", synth.network_json(10, [20], 8), 37, list(range(4, 41)), 8, 0),
+    ("mid_blstm_250", synth.network_json(41, [250], 33), 12, [5, 7, 9, 9, 10, 12, 12, 12, 13, 13, 14, 14], 33, 0),
+]
+
+
+def check_net(oracle, gpu_ctx, net_json, S, lengths, classes, tsize, seed=11, ce=False, tol=STRICT_TOL):
+    import currennt_b200 as cb
+    weights, frac = small_case(oracle, net_json, S, lengths, seed=seed, classes=classes, target_size=tsize)
+    if ce:
+        t = np.abs(frac.targets) + 0.1
+        frac.targets[:] = t / t.sum(1, keepdims=True)
+    maxT = max(lengths) + 2
+    orc, gpu = oracle.OracleNet(net_json, S, maxT), cb.Net(gpu_ctx, net_json, S, maxT)
+    o, g = run_net(orc, weights, frac), run_net(gpu, weights, frac)
+    assert abs(g["error"] - o["error"]) <= tol * abs(o["error"]) + 1e-10
+    layers = json.loads(net_json)["layers"]
+    if layers[-1]["type"] == "multiclass_classification":
+        assert gpu.count_correct() == orc.count_correct()
+    worst = 0.0
+    valid = frac.pat_types != 0
+    for i, ly in enumerate(layers[:-1]):
+        a, b = gpu.get_outputs(i), orc.get_outputs(i)
+        # outputs of padded patterns in a softmax layer are the raw activations (SoftmaxLayer.cu:74-75): same rule on both sides
+        r = rel_err(a, b); worst = max(worst, r)
+        assert r <= tol, ("outputs", i, ly["type"], r)
+        if i > 0:
+            r = rel_err(gpu.get_output_errors(i), orc.get_output_errors(i)); worst = max(worst, r)
+            assert r <= tol, ("outputErrors", i, ly["type"], r)
+            r = rel_err(gpu.get_weight_updates(i), orc.get_weight_updates(i)); worst = max(worst, r)
+            assert r <= tol, ("weightUpdates", i, ly["type"], r)
+        if ly["type"] in ("lstm", "blstm"):
+            ndir = 2 if ly["type"] == "blstm" else 1
+            for d in range(ndir):
+                for which in range(10):
+                    a, b = gpu.lstm_internal(i, d, which), orc.lstm_internal(i, d, which)
+                    if which in (0, 2, 3, 4, 5):
+                        # forward internals of padded slots are unobservable stale values in the reference
+                        # (LstmLayer.cu:78-85 skips them); compare valid slots only
+                        a, b = a[valid], b[valid]
+                    r = rel_err(a, b); worst = max(worst, r)
+                    assert r <= tol, ("internal", i, d, which, r)
+    # padded outputs of every hidden lstm layer are exact zeros
+    for i, ly in enumerate(layers[:-1]):
+        if ly["type"] in ("lstm", "blstm") and frac.Tmin < frac.T:
+            pad_rows = gpu.get_outputs(i)[(~valid) & (np.arange(frac.N) // S >= frac.Tmin)]
+            assert not pad_rows.any()
+    return worst
+
+
+@pytest.mark.parametrize("case", NET_CASES, ids=[c[0] for c in NET_CASES])
+def test_network_forward_backward_parity(oracle, gpu_ctx, case):
+    name, net_json, S, lengths, classes, tsize = case
+    worst = check_net(oracle, gpu_ctx, net_json, S, lengths, classes, tsize, ce=(name == "ce_softmax"))
+    print(name, "worst rel err %.2e" % worst)
+
+
+@pytest.mark.parametrize("G", [1, 2, 3])
+def test_sequence_group_geometries(oracle, gpu_ctx, G, monkeypatch):
+    """The persistent kernels must give the same result for every (sequence groups x cell slices) decomposition."""
+    monkeypatch.setenv("BLSTM_FWD_G", str(G))
+    monkeypatch.setenv("BLSTM_BWD_G", str(G))
+    net_json = synth.network_json(11, [34, ("lstm", 21)], 9)
+    worst = check_net(oracle, gpu_ctx, net_json, 9, [2, 5, 6, 6, 8, 11, 11, 12, 13], 9, 0, seed=5)
+    print("G=%d worst rel err %.2e" % (G, worst))
+
+
+def test_repeated_fractions_reuse_buffers(oracle, gpu_ctx):
+    """A long fraction followed by a shorter one: stale tails of the previous fraction must not leak (Layer.cpp:134-141)."""
+    import currennt_b200 as cb
+    net_json = synth.network_json(6, [10], 4)
+    S = 3
+    w, f_long = small_case(oracle, net_json, S, [9, 10, 12], seed=3, classes=4)
+    _, f_short = small_case(oracle, net_json, S, [2, 4, 5], seed=4, classes=4)
+    orc, gpu = oracle.OracleNet(net_json, S, 14), cb.Net(gpu_ctx, net_json, S, 14)
+    for f in (f_long, f_short, f_long):
+        o, g = run_net(orc, w, f), run_net(gpu, w, f)
+        assert abs(o["error"] - g["error"]) <= STRICT_TOL * abs(o["error"])
+        for i in (1, 2):
+            assert rel_err(gpu.get_weight_updates(i), orc.get_weight_updates(i)) <= STRICT_TOL
+
+
+def test_optimizer_steps_match_oracle(oracle, gpu_ctx):
+    """Three stochastic steps (lr 1e-4 would be invisible in fp32 noise; use 1e-2): weights and momentum state track the oracle."""
+    import currennt_b200 as cb
+    net_json = synth.network_json(8, [12, 10], 6)
+    S, lr, mom = 4, 1e-2, 0.9
+    lengths = [3, 5, 6, 6, 7, 9, 9, 10, 11, 12, 12, 13]
+    xs, cs, _ = synth.make_sequences(lengths, 8, 31, classes=6)
+    weights = synth.init_weights(net_json, 32)
+    orc, gpu = oracle.OracleNet(net_json, S, 16), cb.Net(gpu_ctx, net_json, S, 16)
+    for i, w in enumerate(weights):
+        if len(w):
+            orc.set_weights(i, w); gpu.set_weights(i, w)
+    opt = cb.Optimizer(gpu, lr, mom, hybrid=True)
+    deltas = [np.zeros_like(w) for w in weights]
+    for step in range(3):
+        f = oracle.make_fraction(xs, S, step * S, seq_classes=cs, O=6)
+        orc.load_fraction(f); orc.forward(); eo = orc.calculate_error(); co = orc.count_correct(); orc.backward()
+        orc.sgd_update(deltas, lr, mom)
+        eg, cg, frames = opt.train_fraction(cb.Fraction(gpu_ctx, f))
+        assert frames == f.valid_frames and cg == co
+        assert abs(eg - eo) <= 1e-5 * abs(eo)
+        for i, w in enumerate(weights):
+            if len(w):
+                assert rel_err(gpu.get_weights(i), orc.get_weights(i)) <= 1e-6
+                assert rel_err(opt.weight_deltas(i), deltas[i]) <= 2e-5
+
+
+def test_weight_file_roundtrip(gpu_ctx):
+    """Export -> parse -> import keeps layers and (to %g precision) weights; layout input | bias | internal (TrainableLayer.cu:211-238)."""
+    import currennt_b200 as cb
+    net_json = synth.network_json(5, [6, ("lstm", 4)], 3)
+    net = cb.Net(gpu_ctx, net_json, 2, 4)
+    doc = json.loads(net.export_json())
+    assert [l["type"] for l in doc["layers"]] == ["input", "blstm", "lstm", "softmax", "multiclass_classification"]
+    assert doc["layers"][1]["bias"] == 1.0 and "bias" not in doc["layers"][0]
+    wsec = doc["weights"]["blstm_0"]
+    assert (len(wsec["input"]), len(wsec["bias"]), len(wsec["internal"])) == (6 * 4 * 5, 6 * 4, 6 * (2 * 6 + 3))
+    net2 = cb.Net(gpu_ctx, json.dumps(doc), 2, 4)
+    for i in range(1, 4):
+        a, b = net.get_weights(i), net2.get_weights(i)
+        assert np.allclose(a, b, rtol=2e-6, atol=0)          # "%g": 6 significant digits
+        flat = np.array(list(doc["weights"][doc["layers"][i]["name"]]["input"]) + list(doc["weights"][doc["layers"][i]["name"]]["bias"])
+                        + list(doc["weights"][doc["layers"][i]["name"]]["internal"]), np.float32)
+        assert np.array_equal(flat, b)
+
+
+def test_error_conventions(gpu_ctx):
+    import currennt_b200 as cb
+    with pytest.raises(RuntimeError, match="Unknown layer type"):
+        cb.Net(gpu_ctx, synth.network_json(4, [("gru", 4)], 3), 2, 4)
+    with pytest.raises(RuntimeError, match="odd layer size"):
+        cb.Net(gpu_ctx, synth.network_json(4, [5], 3), 2, 4)
+    with pytest.raises(RuntimeError, match="Not enough layers"):
+        cb.Net(gpu_ctx, json.dumps({"layers": [{"name": "i", "type": "input", "size": 3}]}), 2, 4)
+    net = cb.Net(gpu_ctx, synth.network_json(4, [6], 3), 2, 4)
+    with pytest.raises(RuntimeError, match="wrong number of weights"):
+        net.set_weights(1, np.zeros(5, np.float32))
