@@ -155,6 +155,11 @@ int bl_sse_error(bl_ctx *ctx, int O, int N, const char *patTypes, const float *t
 int bl_sse_backward(bl_ctx *ctx, int O, int N, const char *patTypes, const float *targets, int ldt,
                     const float *Y, int ldy, float *dY, int lddy);
 
+/* Elementwise evaluation of the scalar functions every kernel shares (parity tests pin them bit-for-bit against
+ * the reference's functors): which = 0 Logistic::fn (Logistic.cuh:33-43), 1 Tanh::fn (Tanh.cuh:33-36),
+ * 2 safeExp (safeExp.cuh:32-40), 3 limitedError (limitedError.cuh:31-34).  x, y device arrays of n floats. */
+int bl_eval_scalar_fn(bl_ctx *ctx, int which, size_t n, const float *x, float *y);
+
 /* ------------------------------------------------------------------ optimizer step
  * UpdateWeightFn (optimizers/SteepestDescentOptimizer.cu:39-59): delta = momentum*delta - lr*grad; w += delta */
 int bl_sgd_update(bl_ctx *ctx, size_t n, float learningRate, float momentum, float *W, const float *dW, float *deltas);

@@ -227,6 +227,14 @@ __global__ void vector_add_kernel(size_t n, const float *__restrict__ x, float *
     for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (size_t)gridDim.x * blockDim.x) y[e] = __fadd_rn(y[e], x[e]);
 }
 
+__global__ void scalar_fn_kernel(int which, size_t n, const float *__restrict__ x, float *__restrict__ y)
+{
+    for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (size_t)gridDim.x * blockDim.x) {
+        const float v = x[e];
+        y[e] = which == 0 ? logistic_fn(v) : which == 1 ? tanh_fn(v) : which == 2 ? safe_exp(v) : limited_error(v);
+    }
+}
+
 static inline int ew_blocks(bl_ctx *ctx, size_t total, int threads)
 {
     size_t b = cdivz(total, threads);
@@ -376,6 +384,15 @@ int bl_sgd_update(bl_ctx *ctx, size_t n, float lr, float mom, float *W, const fl
     if (!n) return 0;
     TimedRegion timed(ctx, 3);
     sgd_kernel<<<ew_blocks(ctx, n, 256), 256, 0, ctx->stream>>>(n, lr, mom, W, dW, deltas);
+    BL_LAUNCHED(ctx);
+    return 0;
+}
+
+int bl_eval_scalar_fn(bl_ctx *ctx, int which, size_t n, const float *x, float *y)
+{
+    if (which < 0 || which > 3) return fail(ctx, "bl_eval_scalar_fn: bad selector");
+    if (!n) return 0;
+    scalar_fn_kernel<<<ew_blocks(ctx, n, 256), 256, 0, ctx->stream>>>(which, n, x, y);
     BL_LAUNCHED(ctx);
     return 0;
 }

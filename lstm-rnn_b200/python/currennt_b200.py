@@ -68,6 +68,9 @@ def libs():
         k.bl_comm_destroy.argtypes = [vp]
         k.bl_allreduce_sum_f32.argtypes = [vp, vp, ctypes.c_size_t]
         k.bl_comm_join.argtypes = [vp]
+        k.bl_eval_scalar_fn.argtypes = [vp, ci, ctypes.c_size_t, vp, vp]
+        k.bl_ctx_timing_enable.argtypes = [vp, ci]
+        k.bl_ctx_timing_read.argtypes = [vp, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_long)]
         k.bl_sgd_update.argtypes = [vp, ctypes.c_size_t, cf, cf, vp, vp, vp]
 
         h.cn_last_error.restype = cp
@@ -170,6 +173,14 @@ class Context:
         self.check(self.k.bl_memcpy_d2h(self.p, out.ctypes.data_as(vp), p, out.nbytes))
         self.sync()
         return out
+
+    def eval_scalar_fn(self, which, x):
+        x = np.ascontiguousarray(x, dtype=np.float32)
+        dx, dy = self.to_device(x), self.malloc(max(x.nbytes, 4))
+        self.check(self.k.bl_eval_scalar_fn(self.p, which, x.size, dx, dy))
+        y = self.to_host(dy, x.shape)
+        self.free(dx); self.free(dy)
+        return y
 
     def gemm(self, transA, transB, m, n, k, A, lda, B, ldb, C, ldc, accumulate=0, mode=0):
         self.check(self.k.bl_gemm_f32(self.p, transA, transB, m, n, k, A, lda, B, ldb, C, ldc, accumulate, mode))

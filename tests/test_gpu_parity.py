@@ -8,11 +8,26 @@ import numpy as np
 import pytest
 
 import synth
-from helpers import rel_err, run_net, small_case
+from helpers import ACT_GRID, rel_err, run_net, small_case
 
 pytestmark = pytest.mark.gpu
 
 STRICT_TOL = 1e-5
+
+
+# ----------------------------------------------------------------------------- scalar functors, bit for bit
+def test_scalar_functions_bit_exact(gpu_ctx, oracle):
+    """Logistic / Tanh / safeExp / limitedError on the device == the reference's host functors (glibc expf) bitwise."""
+    L = oracle.oracle_lib()
+    rng = np.random.default_rng(0)
+    x = np.concatenate([rng.standard_normal(200000) * s for s in (1e-3, 0.1, 1.0, 5.0, 30.0)] +
+                       [np.array([0.0, -0.0, 88.7, -88.7, 88.722839, -88.722839, 89.0, -89.0, 100.0, -104.0, 1e-30, -1e30, 44.36, -44.36])]).astype(np.float32)
+    for which, fn in enumerate((L.orc_logistic, L.orc_tanh, L.orc_safe_exp, L.orc_limited_error)):
+        got = gpu_ctx.eval_scalar_fn(which, x)
+        want = np.array([fn(float(v)) for v in x[::37]], np.float32)     # python-loop oracle on a strided sample
+        assert np.array_equal(got[::37].view(np.uint32), want.view(np.uint32)), which
+        tail = np.array([fn(float(v)) for v in x[-14:]], np.float32)
+        assert np.array_equal(got[-14:].view(np.uint32), tail.view(np.uint32)), which
 
 
 # ----------------------------------------------------------------------------- GEMM (helpers::Matrix drop-in)
@@ -102,7 +117,7 @@ def check_net(oracle, gpu_ctx, net_json, S, lengths, classes, tsize, seed=11, ce
     for i, ly in enumerate(layers[:-1]):
         a, b = gpu.get_outputs(i), orc.get_outputs(i)
         # outputs of padded patterns in a softmax layer are the raw activations (SoftmaxLayer.cu:74-75): same rule on both sides
-        r = rel_err(a, b); worst = max(worst, r)
+        r = rel_err(a, b, atol=ACT_GRID); worst = max(worst, r)
         assert r <= tol, ("outputs", i, ly["type"], r)
         if i > 0:
             r = rel_err(gpu.get_output_errors(i), orc.get_output_errors(i)); worst = max(worst, r)
@@ -200,7 +215,7 @@ def test_weight_file_roundtrip(gpu_ctx):
     net2 = cb.Net(gpu_ctx, json.dumps(doc), 2, 4)
     for i in range(1, 4):
         a, b = net.get_weights(i), net2.get_weights(i)
-        assert np.allclose(a, b, rtol=2e-6, atol=0)          # "%g": 6 significant digits
+        assert np.allclose(a, b, rtol=5.1e-6, atol=0)        # "%g": 6 significant digits
         flat = np.array(list(doc["weights"][doc["layers"][i]["name"]]["input"]) + list(doc["weights"][doc["layers"][i]["name"]]["bias"])
                         + list(doc["weights"][doc["layers"][i]["name"]]["internal"]), np.float32)
         assert np.array_equal(flat, b)
