@@ -120,6 +120,9 @@ int bl_lstm_backward(bl_lstm_plan *plan, const float *W, const float *X, int ldx
 /* Gathers an internal tensor into the reference's [T*S][H] layout (LstmLayer.hpp:169-232 accessors):
  * which: 0 cellStates 1 cellStateErrors 2 niActs 3 igActs 4 fgActs 5 ogActs 6 niDeltas 7 igDeltas 8 fgDeltas 9 ogDeltas */
 int bl_lstm_get_internal(bl_lstm_plan *plan, int dir, int which, int T, float *dst);
+/* Tuning aid (BLSTM_REC_TRACE=1 at plan creation): per-CTA, per-step clock64 stamps of the forward persistent kernel,
+ * [rows][T][6] = {step start, counter seen, exchange copied, GEMM done, gate math done, published}. */
+int bl_lstm_debug_trace(bl_lstm_plan *plan, int T, long long *host_dst, int *rows);
 /* Launch geometry chosen for the persistent kernels: out[0..3] = fwd {G seq groups, C cell slices, cells/CTA, smem bytes},
  * out[4..7] = bwd likewise. */
 int bl_lstm_plan_info(const bl_lstm_plan *plan, int *out8);

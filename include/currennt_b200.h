@@ -39,6 +39,7 @@ int     cn_layer_get_output_errors(cn_net *net, int layer, float *host_dst, long
 /* [T*S][H] host copy of an LSTM-internal tensor; `which` as bl_lstm_get_internal */
 int     cn_lstm_get_internal(cn_net *net, int layer, int dir, int which, float *host_dst, long n);
 int     cn_lstm_plan_info(cn_net *net, int layer, int *out8);
+int     cn_lstm_debug_trace(cn_net *net, int layer, int T, long long *host_dst, int *rows);
 /* serialises {"layers":..., "weights":...} (NeuralNetwork.cpp:192-235); returns the length needed (incl. NUL) */
 long    cn_net_export_json(cn_net *net, char *buf, long cap);
 

@@ -25,6 +25,7 @@ struct bl_lstm_plan {
     float bias;
     bl::RecGeom gf, gb;
     float *acts, *deltas, *cst, *cerr, *hx, *dx, *gpart;
+    long long *trace;
     unsigned *flags_f, *flags_b;
     int gsplit;
     int lastT;
@@ -110,11 +111,13 @@ int bl_lstm_plan_create(bl_ctx *ctx, int P, int L, int bidirectional, int S, int
     pl->S = S; pl->maxT = maxT; pl->bias = bias; pl->lastT = 0;
     pl->acts = pl->deltas = pl->cst = pl->cerr = pl->hx = pl->dx = pl->gpart = nullptr;
     pl->flags_f = pl->flags_b = nullptr;
+    pl->trace = nullptr;
 
     const int cap = ctx->smem_optin - 1024;
-    const char *ef = getenv("BLSTM_FWD_G"), *eb = getenv("BLSTM_BWD_G");
-    if (!bl::choose_geometry(false, pl->H, S, pl->ndir, ctx->num_sms, cap, ef ? atoi(ef) : 0, &pl->gf) ||
-        !bl::choose_geometry(true, pl->H, S, pl->ndir, ctx->num_sms, cap, eb ? atoi(eb) : 0, &pl->gb)) {
+    // tuning overrides (tools/sweep_geometry.py): sequence groups and sub-CTAs per CTA of either kernel
+    const char *ef = getenv("BLSTM_FWD_G"), *eb = getenv("BLSTM_BWD_G"), *nf = getenv("BLSTM_FWD_NSUB"), *nb = getenv("BLSTM_BWD_NSUB");
+    if (!bl::choose_geometry(false, pl->H, S, pl->ndir, ctx->num_sms, cap, ef ? atoi(ef) : 0, nf ? atoi(nf) : 0, &pl->gf) ||
+        !bl::choose_geometry(true, pl->H, S, pl->ndir, ctx->num_sms, cap, eb ? atoi(eb) : 0, nb ? atoi(nb) : 0, &pl->gb)) {
         delete pl;
         return bl::fail(ctx, "bl_lstm_plan_create: no persistent-kernel geometry fits (H=%d S=%d): recurrent weights do not fit in shared memory",
                         L / (bidirectional ? 2 : 1), S);
@@ -132,6 +135,8 @@ int bl_lstm_plan_create(bl_ctx *ctx, int P, int L, int bidirectional, int S, int
     rc |= bl_malloc(ctx, (void **)&pl->gpart, (size_t)pl->gsplit * 7 * L * sizeof(float));
     rc |= bl_malloc(ctx, (void **)&pl->flags_f, (size_t)pl->ndir * pl->gf.G * 32 * sizeof(unsigned));
     rc |= bl_malloc(ctx, (void **)&pl->flags_b, (size_t)pl->ndir * pl->gb.G * 32 * sizeof(unsigned));
+    if (getenv("BLSTM_REC_TRACE"))
+        rc |= bl_malloc(ctx, (void **)&pl->trace, (size_t)ctx->num_sms * 4 * maxT * 6 * sizeof(long long));
     if (rc) { bl_lstm_plan_destroy(pl); return 1; }
     // zero-filled like the reference's buffers (LstmLayer.cu:554); the exchange buffers' padding columns must stay zero
     rc |= bl_memset(ctx, pl->acts, 0, N * 4 * L * sizeof(float));
@@ -149,15 +154,15 @@ void bl_lstm_plan_destroy(bl_lstm_plan *pl)
 {
     if (!pl) return;
     cudaStreamSynchronize(pl->ctx->stream);
-    void *bufs[] = { pl->acts, pl->deltas, pl->cst, pl->cerr, pl->hx, pl->dx, pl->gpart, pl->flags_f, pl->flags_b };
+    void *bufs[] = { pl->acts, pl->deltas, pl->cst, pl->cerr, pl->hx, pl->dx, pl->gpart, pl->flags_f, pl->flags_b, pl->trace };
     for (void *b : bufs) if (b) cudaFree(b);
     delete pl;
 }
 
 int bl_lstm_plan_info(const bl_lstm_plan *pl, int *o)
 {
-    o[0] = pl->gf.G; o[1] = pl->gf.C; o[2] = pl->gf.CL; o[3] = (int)pl->gf.smem;
-    o[4] = pl->gb.G; o[5] = pl->gb.C; o[6] = pl->gb.CL; o[7] = (int)pl->gb.smem;
+    o[0] = pl->gf.G; o[1] = pl->gf.C; o[2] = pl->gf.CL; o[3] = (int)pl->gf.smem + pl->gf.nsub;     // smem is a multiple of 4: low bits carry nsub
+    o[4] = pl->gb.G; o[5] = pl->gb.C; o[6] = pl->gb.CL; o[7] = (int)pl->gb.smem + pl->gb.nsub;
     return 0;
 }
 
@@ -175,7 +180,7 @@ int bl_lstm_forward(bl_lstm_plan *pl, const float *W, const float *X, int ldx, c
     bl::RecFwdParams p;
     p.Wb = W + (size_t)4 * L * P; p.Wi = p.Wb + 4 * L; p.Wp = p.Wi + (size_t)4 * L * H;
     p.acts = pl->acts; p.cst = pl->cst; p.Y = Y; p.ldy = ldy; p.hx = pl->hx; p.flags = pl->flags_f; p.pat = patTypes;
-    p.T = T; p.Tmin = Tmin; p.S = S; p.H = H; p.L = L; p.ndir = pl->ndir; p.bias = pl->bias; p.g = pl->gf;
+    p.T = T; p.Tmin = Tmin; p.S = S; p.H = H; p.L = L; p.ndir = pl->ndir; p.bias = pl->bias; p.g = pl->gf; p.trace = pl->trace;
     BL_CHECK(bl::launch_lstm_fwd(ctx, p));
     pl->lastT = T;
     return 0;
@@ -235,6 +240,17 @@ int bl_lstm_backward(bl_lstm_plan *pl, const float *W, const float *X, int ldx, 
         bl::lstm_small_grads_finish_kernel<<<bl::cdiv(7 * L, 256), 256, 0, ctx->stream>>>(L, nsplit, pl->gpart, dWbias, dWpeep);
         BL_LAUNCHED(ctx);
     }
+    return 0;
+}
+
+// tuning aid: copies the forward kernel's clock64 trace ([CTAs*nsub][T][6]) to the host; returns the number of rows via *rows
+int bl_lstm_debug_trace(bl_lstm_plan *pl, int T, long long *host_dst, int *rows)
+{
+    if (!pl->trace) return bl::fail(pl->ctx, "tracing is off (set BLSTM_REC_TRACE before creating the plan)");
+    const int n = pl->ndir * (pl->gf.G / pl->gf.nsub) * pl->gf.C * pl->gf.nsub;
+    *rows = n;
+    BL_CUDA(pl->ctx, cudaMemcpyAsync(host_dst, pl->trace, (size_t)n * T * 6 * sizeof(long long), cudaMemcpyDeviceToHost, pl->ctx->stream));
+    BL_CUDA(pl->ctx, cudaStreamSynchronize(pl->ctx->stream));
     return 0;
 }
 

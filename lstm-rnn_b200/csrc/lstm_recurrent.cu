@@ -34,50 +34,61 @@ static int hpad_of(int H)
     return h;
 }
 
-bool choose_geometry(bool bwd, int H, int S, int ndir, int num_sms, int smem_cap, int forceG, RecGeom *out)
+bool choose_geometry(bool bwd, int H, int S, int ndir, int num_sms, int smem_cap, int forceG, int forceNsub, RecGeom *out)
 {
     const int Hpad = hpad_of(H);
     bool found = false;
     RecGeom best{};
     const int per_dir = num_sms / ndir;
-    for (int G = 1; G <= 16 && G <= S; ++G) {
-        if (forceG > 0 && G != forceG) continue;
-        int C = per_dir / G;
-        if (C < 1) break;
-        const int CL = cdiv(H, C);
-        C = cdiv(H, CL);
-        const int SG = cdiv(S, G);
-        if (cdiv(S, SG) != G) continue;                         // same SG as a smaller G
-        if (CL * SG > REC_NPAIR * REC_NT) continue;
-        const int R = bwd ? CL : 4 * CL;
-        const int RQ = cdiv(R, 4), SQ = cdiv(SG, 4);
-        const int K = bwd ? 4 * Hpad : Hpad, K4 = K / 4;
-        const int RS = bwd ? 4 * Hpad + 4 : Hpad;
-        for (int LR = 1; LR <= 32; LR *= 2) {
-            const int LS = 32 / LR;
-            const int WR = cdiv(RQ, LR), WS = cdiv(SQ, LS);
-            const int tasks = WR * WS;
-            int KS = REC_NW / tasks; if (KS < 1) KS = 1;
-            while (KS > 1 && K4 / KS < 8) --KS;
-            const int KB4 = cdiv(K4, KS);
-            const int Rpad = 4 * WR * LR, Spad = 4 * WS * LS;
-            const int RP = Rpad | 1;
-            const size_t smem = ((size_t)(Rpad + Spad) * RS + (size_t)KS * Spad * RP) * sizeof(float);
-            if ((int)smem > smem_cap) continue;
-            // cost model (cycles per step): issue slots vs shared-memory wavefronts of the GEMM + exchange copy
-            const double iters = (double)tasks * KS * KB4;                       // warp-iterations, 64 FFMA + 8 LDS.128 each
-            const double issue = iters * 76.0 / 4.0;                             // 4 schedulers
-            const double wave  = iters * 4.0 * ((LR > 8 ? LR / 8 : 1) + (LS > 8 ? LS / 8 : 1));
-            const double copy  = (double)SG * K * 4.0 / 48.0;                    // ~48 B/clk/SM from L2
-            const double sync  = 1500.0 + 12.0 * C;                              // counter round trip grows with the slice count
-            const double cost  = (issue > wave ? issue : wave) + copy + sync;
-            if (!found || cost < best.cost) {
-                found = true;
-                best.G = G; best.C = C; best.CL = CL; best.SG = SG; best.R = R;
-                best.LR = LR; best.LS = LS; best.LSlog = (int)std::lround(std::log2((double)LS));
-                best.WR = WR; best.WS = WS; best.KS = KS; best.RQt = WR * LR; best.SQt = WS * LS;
-                best.Rpad = Rpad; best.Spad = Spad; best.K4 = K4; best.KB4 = KB4; best.RS = RS; best.RP = RP;
-                best.Hpad = Hpad; best.smem = smem; best.cost = cost;
+    for (int nsub = 1; nsub <= 4; nsub *= 2) {
+        if (forceNsub > 0 && nsub != forceNsub) continue;
+        const int nt = REC_NT / nsub, nw = nt / 32;
+        for (int Gc = 1; Gc <= 16 && Gc * nsub <= S; ++Gc) {          // Gc: sequence groups at CTA level
+            const int G = Gc * nsub;
+            if (forceG > 0 && G != forceG) continue;
+            int C = per_dir / Gc;
+            if (C < 1) break;
+            const int CL = cdiv(H, C);
+            C = cdiv(H, CL);
+            const int SG = cdiv(S, G);
+            if (cdiv(S, SG) != G) continue;                             // trailing groups would be empty
+            if (CL * SG > REC_NPAIR * nt) continue;
+            const int R = bwd ? CL : 4 * CL;
+            const int RQ = cdiv(R, 4), SQ = cdiv(SG, 4);
+            const int K = bwd ? 4 * Hpad : Hpad, K4 = K / 4;
+            const int RS = bwd ? 4 * Hpad + 4 : Hpad;
+            for (int LR = 1; LR <= 32; LR *= 2) {
+                const int LS = 32 / LR;
+                const int WR = cdiv(RQ, LR), WS = cdiv(SQ, LS);
+                const int tasks = WR * WS;
+                int KS = nw / tasks; if (KS < 1) KS = 1;
+                while (KS > 1 && K4 / KS < 8) --KS;
+                const int KB4 = cdiv(K4, KS);
+                const int Rpad = 4 * WR * LR, Spad = 4 * WS * LS;
+                const int RP = Rpad | 1;
+                const size_t smem = ((size_t)Rpad * RS + (size_t)nsub * ((size_t)Spad * RS + (size_t)KS * Spad * RP)) * sizeof(float);
+                if ((int)smem > smem_cap) continue;
+                // cost model (cycles per step).  The sub-CTAs of an SM share its FFMA issue slots and shared-memory
+                // bandwidth, so their GEMM phases add up; the latency chain of one group (counter round trip, exchange
+                // copy, its own GEMM, gate math, publish) overlaps the other groups' GEMMs.
+                const double passes = (double)cdiv(tasks * KS, nw);
+                const double iters = (double)tasks * KS * KB4;                   // warp-iterations of one group, 64 FFMA + 8 LDS.128 each
+                const double issue = iters * 76.0 / 4.0;
+                const double wave  = iters * 4.0 * ((LR > 8 ? LR / 8 : 1) + (LS > 8 ? LS / 8 : 1));
+                const double gemm1 = (issue > wave ? issue : wave);
+                const double lat1  = passes * KB4 * 76.0 * 1.6;                  // one warp's serial path through its tasks
+                const double copy  = (double)SG * K * 4.0 / 48.0 + 600.0;
+                const double chain = 3500.0 + 10.0 * C + copy + (lat1 > gemm1 ? lat1 : gemm1) + 900.0;
+                const double busy  = nsub * (gemm1 + 400.0);
+                const double cost  = busy > chain ? busy : chain;
+                if (!found || cost < best.cost) {
+                    found = true;
+                    best.G = G; best.C = C; best.CL = CL; best.SG = SG; best.R = R; best.nsub = nsub;
+                    best.LR = LR; best.LS = LS; best.LSlog = (int)std::lround(std::log2((double)LS));
+                    best.WR = WR; best.WS = WS; best.KS = KS; best.RQt = WR * LR; best.SQt = WS * LS;
+                    best.Rpad = Rpad; best.Spad = Spad; best.K4 = K4; best.KB4 = KB4; best.RS = RS; best.RP = RP;
+                    best.Hpad = Hpad; best.smem = smem; best.cost = cost;
+                }
             }
         }
     }
@@ -93,19 +104,27 @@ __device__ __forceinline__ unsigned ld_acquire_u32(const unsigned *p)
     return v;
 }
 
-__device__ __forceinline__ void wait_counter(const unsigned *flag, unsigned target)
+// barrier over one sub-CTA (named barrier sub+1; barrier 0 stays the whole-CTA __syncthreads)
+__device__ __forceinline__ void bar_sub(int sub, int nt)
 {
-    if (threadIdx.x == 0) {
-        while (ld_acquire_u32(flag) < target) { }
-    }
-    __syncthreads();
+    asm volatile("bar.sync %0, %1;" :: "r"(sub + 1), "r"(nt) : "memory");
 }
 
-__device__ __forceinline__ void publish(unsigned *flag)
+// Step-counter protocol (the one cooperative-groups grid sync uses, restricted to the C slices of one sequence group):
+// producer: all stores -> sub-CTA barrier -> ONE thread: __threadfence (cumulative over what the barrier ordered) + atomicAdd
+// consumer: ONE thread: acquire-load spin -> sub-CTA barrier -> everybody reads the exchange buffer through L2 (ld.global.cg)
+__device__ __forceinline__ void wait_counter(const unsigned *flag, unsigned target, int ts, int sub, int nt)
 {
-    __threadfence();                 // every thread: its stores are visible device-wide before the barrier
-    __syncthreads();
-    if (threadIdx.x == 0) {
+    if (ts == 0) {
+        while (ld_acquire_u32(flag) < target) { }
+    }
+    bar_sub(sub, nt);
+}
+
+__device__ __forceinline__ void publish(unsigned *flag, int ts, int sub, int nt)
+{
+    bar_sub(sub, nt);
+    if (ts == 0) {
         __threadfence();
         atomicAdd(flag, 1u);
     }
@@ -113,11 +132,11 @@ __device__ __forceinline__ void publish(unsigned *flag)
 
 // rows x sequences x K product out of shared memory; partial sums (one per K split) into `stage`.
 __device__ __forceinline__ void smem_gemm(const RecGeom &g, const float *__restrict__ Wsm, const float *__restrict__ tile,
-                                          float *__restrict__ stage, int warp, int lane)
+                                          float *__restrict__ stage, int warp, int lane, int nw)
 {
     const int tasks = g.WR * g.WS * g.KS;
     const int lr = lane >> g.LSlog, ls = lane & (g.LS - 1);
-    for (int wt = warp; wt < tasks; wt += REC_NW) {
+    for (int wt = warp; wt < tasks; wt += nw) {
         const int ks = wt % g.KS, tl = wt / g.KS;
         const int wr = tl % g.WR, ws = tl / g.WR;
         const int rq = wr * g.LR + lr, sq = ws * g.LS + ls;
@@ -169,21 +188,24 @@ __global__ void __launch_bounds__(REC_NT, 1) lstm_fwd_persistent_kernel(const Re
 {
     extern __shared__ __align__(16) float smem[];
     const RecGeom &g = p.g;
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int nt = REC_NT / g.nsub, nw = nt >> 5;                 // threads / warps per sub-CTA
+    const int sub = tid / nt, ts = tid - sub * nt, warp = ts >> 5;
     float *Wsm = smem;
-    float *tile = Wsm + (size_t)g.Rpad * g.RS;
-    float *stage = tile + (size_t)g.Spad * g.RS;
+    float *tile = Wsm + (size_t)g.Rpad * g.RS + (size_t)sub * g.Spad * g.RS;
+    float *stage = Wsm + (size_t)g.Rpad * g.RS + (size_t)g.nsub * g.Spad * g.RS + (size_t)sub * g.KS * g.Spad * g.RP;
 
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int H = p.H, L = p.L, S = p.S, T = p.T;
-    const int d = blockIdx.x / (g.G * g.C);
-    const int grp = (blockIdx.x % (g.G * g.C)) / g.C;
+    const int Gc = g.G / g.nsub;                                   // sequence groups at CTA level
+    const int d = blockIdx.x / (Gc * g.C);
+    const int grp = ((blockIdx.x % (Gc * g.C)) / g.C) * g.nsub + sub;
     const int cs = blockIdx.x % g.C;
     const int j0 = cs * g.CL, ncell = min(g.CL, H - j0);
     const int s0 = grp * g.SG, nseq = min(g.SG, S - s0);
     unsigned *flag = p.flags + (size_t)(d * g.G + grp) * 32;
 
     // one-time: zero both operand tiles (padding rows/columns stay zero), then the weight slice.
-    for (int i = tid; i < (g.Rpad + g.Spad) * g.RS; i += REC_NT) smem[i] = 0.0f;
+    for (int i = tid; i < (int)(g.smem / sizeof(float)); i += REC_NT) smem[i] = 0.0f;
     __syncthreads();
     // Wsm row (gate*CL + cell) = column (d*H + j) of the gate's internal matrix: contiguous over the source cell k
     // (weight layout internal: g*L*H + d*H*H + j*H + k, LstmLayer.cu:586-596)
@@ -199,7 +221,7 @@ __global__ void __launch_bounds__(REC_NT, 1) lstm_fwd_persistent_kernel(const Re
     float wb[REC_NPAIR][4], wpe[REC_NPAIR][3], cprev[REC_NPAIR];
 #pragma unroll
     for (int u = 0; u < REC_NPAIR; ++u) {
-        const int pr = tid + u * REC_NT;
+        const int pr = ts + u * nt;
         cl_[u] = pr % g.CL; sl_[u] = pr / g.CL;
         valid[u] = (cl_[u] < ncell) && (sl_[u] < nseq);
         cprev[u] = 0.0f;
@@ -212,6 +234,7 @@ __global__ void __launch_bounds__(REC_NT, 1) lstm_fwd_persistent_kernel(const Re
         }
     }
     __syncthreads();
+    if (nseq <= 0) return;                                       // (cannot happen with the planner's G; keeps named barriers consistent)
 
     for (int q = 0; q < T; ++q) {
         const int t = (d == 0) ? q : T - 1 - q;
@@ -232,15 +255,20 @@ __global__ void __launch_bounds__(REC_NT, 1) lstm_fwd_persistent_kernel(const Re
             }
         }
 
+        long long *tr = p.trace ? p.trace + ((size_t)(blockIdx.x * g.nsub + sub) * T + q) * 6 : nullptr;
+        if (tr && ts == 0) tr[0] = clock64();
         if (!first) {
-            wait_counter(flag, (unsigned)(g.C * q));
+            wait_counter(flag, (unsigned)(g.C * q), ts, sub, nt);
+            if (tr && ts == 0) tr[1] = clock64();
             const float4 *src = reinterpret_cast<const float4 *>(p.hx + ((size_t)(d * 2 + ((q - 1) & 1)) * S + s0) * g.Hpad);
             float4 *dst = reinterpret_cast<float4 *>(tile);
             const int n4 = nseq * g.Hpad / 4;
-            for (int i = tid; i < n4; i += REC_NT) dst[i] = __ldcg(src + i);
-            __syncthreads();
-            smem_gemm(g, Wsm, tile, stage, warp, lane);
-            __syncthreads();
+            for (int i = ts; i < n4; i += nt) dst[i] = __ldcg(src + i);
+            bar_sub(sub, nt);
+            if (tr && ts == 0) tr[2] = clock64();
+            smem_gemm(g, Wsm, tile, stage, warp, lane, nw);
+            bar_sub(sub, nt);
+            if (tr && ts == 0) tr[3] = clock64();
         }
 
 #pragma unroll
@@ -281,7 +309,9 @@ __global__ void __launch_bounds__(REC_NT, 1) lstm_fwd_persistent_kernel(const Re
             p.Y[n * p.ldy + col] = h;
             p.hx[((size_t)(d * 2 + (q & 1)) * S + s0 + sl_[u]) * g.Hpad + j0 + cl_[u]] = h;
         }
-        if (q + 1 < T) publish(flag);
+        if (tr && ts == 0) tr[4] = clock64();
+        if (q + 1 < T) publish(flag, ts, sub, nt);
+        if (tr && ts == 0) tr[5] = clock64();
     }
 }
 
@@ -290,21 +320,24 @@ __global__ void __launch_bounds__(REC_NT, 1) lstm_bwd_persistent_kernel(const Re
 {
     extern __shared__ __align__(16) float smem[];
     const RecGeom &g = p.g;
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int nt = REC_NT / g.nsub, nw = nt >> 5;                 // threads / warps per sub-CTA
+    const int sub = tid / nt, ts = tid - sub * nt, warp = ts >> 5;
     float *Wsm = smem;
-    float *tile = Wsm + (size_t)g.Rpad * g.RS;
-    float *stage = tile + (size_t)g.Spad * g.RS;
+    float *tile = Wsm + (size_t)g.Rpad * g.RS + (size_t)sub * g.Spad * g.RS;
+    float *stage = Wsm + (size_t)g.Rpad * g.RS + (size_t)g.nsub * g.Spad * g.RS + (size_t)sub * g.KS * g.Spad * g.RP;
 
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int H = p.H, L = p.L, S = p.S, T = p.T;
-    const int d = blockIdx.x / (g.G * g.C);
-    const int grp = (blockIdx.x % (g.G * g.C)) / g.C;
+    const int Gc = g.G / g.nsub;                                   // sequence groups at CTA level
+    const int d = blockIdx.x / (Gc * g.C);
+    const int grp = ((blockIdx.x % (Gc * g.C)) / g.C) * g.nsub + sub;
     const int cs = blockIdx.x % g.C;
     const int j0 = cs * g.CL, ncell = min(g.CL, H - j0);
     const int s0 = grp * g.SG, nseq = min(g.SG, S - s0);
     unsigned *flag = p.flags + (size_t)(d * g.G + grp) * 32;
     const bool inplace = (p.ndir == 1);
 
-    for (int i = tid; i < (g.Rpad + g.Spad) * g.RS; i += REC_NT) smem[i] = 0.0f;
+    for (int i = tid; i < (int)(g.smem / sizeof(float)); i += REC_NT) smem[i] = 0.0f;
     __syncthreads();
     // Wsm row (cell k) = [gate][target cell j] : W_gate[k, j] = Wi[gate*L*H + d*H*H + j*H + k]  (the (N,N) products of :939-942)
     for (int idx = tid; idx < 4 * H * ncell; idx += REC_NT) {
@@ -319,7 +352,7 @@ __global__ void __launch_bounds__(REC_NT, 1) lstm_bwd_persistent_kernel(const Re
     float nfg[REC_NPAIR], ncerr[REC_NPAIR], ndig[REC_NPAIR], ndfg[REC_NPAIR];   // "next step" state, :253-256
 #pragma unroll
     for (int u = 0; u < REC_NPAIR; ++u) {
-        const int pr = tid + u * REC_NT;
+        const int pr = ts + u * nt;
         cl_[u] = pr % g.CL; sl_[u] = pr / g.CL;
         valid[u] = (cl_[u] < ncell) && (sl_[u] < nseq);
         nfg[u] = ncerr[u] = ndig[u] = ndfg[u] = 0.0f;
@@ -330,6 +363,7 @@ __global__ void __launch_bounds__(REC_NT, 1) lstm_bwd_persistent_kernel(const Re
         }
     }
     __syncthreads();
+    if (nseq <= 0) return;                                       // (cannot happen with the planner's G; keeps named barriers consistent)
 
     for (int q = 0; q < T; ++q) {
         // the fw direction walks time backwards, the bw direction forwards (:936, :970)
@@ -356,14 +390,14 @@ __global__ void __launch_bounds__(REC_NT, 1) lstm_bwd_persistent_kernel(const Re
         }
 
         if (!firstCall) {
-            wait_counter(flag, (unsigned)(g.C * q));
+            wait_counter(flag, (unsigned)(g.C * q), ts, sub, nt);
             const float4 *src = reinterpret_cast<const float4 *>(p.dx + ((size_t)(d * 2 + ((q - 1) & 1)) * S + s0) * g.RS);
             float4 *dst = reinterpret_cast<float4 *>(tile);
             const int n4 = nseq * g.RS / 4;
-            for (int i = tid; i < n4; i += REC_NT) dst[i] = __ldcg(src + i);
-            __syncthreads();
-            smem_gemm(g, Wsm, tile, stage, warp, lane);
-            __syncthreads();
+            for (int i = ts; i < n4; i += nt) dst[i] = __ldcg(src + i);
+            bar_sub(sub, nt);
+            smem_gemm(g, Wsm, tile, stage, warp, lane, nw);
+            bar_sub(sub, nt);
         }
 
 #pragma unroll
@@ -400,7 +434,7 @@ __global__ void __launch_bounds__(REC_NT, 1) lstm_bwd_persistent_kernel(const Re
             float *xp = p.dx + ((size_t)(d * 2 + (q & 1)) * S + s0 + sl_[u]) * g.RS + j0 + cl_[u];
             xp[0] = dni; xp[g.Hpad] = dig; xp[2 * g.Hpad] = dfg; xp[3 * g.Hpad] = dog;
         }
-        if (q + 1 < T) publish(flag);
+        if (q + 1 < T) publish(flag, ts, sub, nt);
     }
 }
 
@@ -409,7 +443,7 @@ template <typename Params, typename Kernel>
 static int launch_persistent(bl_ctx *ctx, Kernel kernel, const Params &p, const char *name)
 {
     const RecGeom &g = p.g;
-    const int grid = p.ndir * g.G * g.C;
+    const int grid = p.ndir * (g.G / g.nsub) * g.C;
     BL_CUDA(ctx, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem));
     int per_sm = 0;
     BL_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, REC_NT, g.smem));

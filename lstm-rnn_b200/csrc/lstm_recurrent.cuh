@@ -11,7 +11,10 @@ constexpr int REC_NPAIR = 2;           // (cell, sequence) pairs per thread in t
 // Launch geometry of one persistent kernel.  One CTA owns CL cells of one direction for the SG sequences of
 // one sequence group; its slice of the recurrent weights stays in shared memory for the whole pass.
 struct RecGeom {
-    int G, C, CL, SG;       // sequence groups, cell slices per (direction, group), cells per CTA, sequences per group
+    int G, C, CL, SG;       // sequence groups (all sub-CTAs counted), cell slices per (direction, group), cells per CTA, sequences per group
+    int nsub;               // sub-CTAs per CTA: each owns one sequence group and has its own barrier and step counter, so one
+                            // group's counter wait / exchange copy overlaps the other groups' FFMA work on the same SM; all
+                            // sub-CTAs share the CTA's weight slice in shared memory.  CTAs per direction = (G / nsub) * C
     int R;                  // GEMM rows per CTA: 4*CL (forward: gate x cell), CL (BPTT: cell)
     int LR, LS, LSlog;      // lanes along row quads / sequence quads (LR*LS == 32)
     int WR, WS, KS;         // warp tiles along rows / sequences, K splits
@@ -25,7 +28,7 @@ struct RecGeom {
     double cost;
 };
 
-bool choose_geometry(bool bwd, int H, int S, int ndir, int num_sms, int smem_cap, int forceG, RecGeom *out);
+bool choose_geometry(bool bwd, int H, int S, int ndir, int num_sms, int smem_cap, int forceG, int forceNsub, RecGeom *out);
 
 struct RecFwdParams {
     const float *Wb, *Wi, *Wp;      // bias / internal / peephole segments of the layer's weight vector
@@ -37,6 +40,7 @@ struct RecFwdParams {
     const char *pat;
     int T, Tmin, S, H, L, ndir;
     float bias;
+    long long *trace;               // optional [CTAs*nsub][T][6] clock64 stamps (BLSTM_REC_TRACE tuning aid), else NULL
     RecGeom g;
 };
 

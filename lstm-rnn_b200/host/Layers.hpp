@@ -137,6 +137,7 @@ public:
     // per-direction variant (extension: lets tests diff blstm internals too)
     std::vector<real_t> internalOfDirection(int dir, int which);
     void planInfo(int *out8) const;
+    bl_lstm_plan *plan() const { return m_plan; }
     virtual void computeForwardPass();
     virtual void computeBackwardPass();
 private:

@@ -357,7 +357,11 @@ class Net:
     def plan_info(self, i):
         out = (ctypes.c_int * 8)()
         self._chk(self.h.cn_lstm_plan_info(self.p, i, out))
-        return dict(zip(("fwd_G", "fwd_C", "fwd_CL", "fwd_smem", "bwd_G", "bwd_C", "bwd_CL", "bwd_smem"), [int(x) for x in out]))
+        d = dict(zip(("fwd_G", "fwd_C", "fwd_CL", "fwd_smem", "bwd_G", "bwd_C", "bwd_CL", "bwd_smem"), [int(x) for x in out]))
+        for k in ("fwd", "bwd"):                      # the low two bits of the (4-byte aligned) smem size carry nsub (1, 2 or 4 -> 1, 2, 0)
+            d[k + "_nsub"] = (d[k + "_smem"] & 3) or 4
+            d[k + "_smem"] &= ~3
+        return d
 
     def export_json(self):
         n = self.h.cn_net_export_json(self.p, None, 0)

@@ -1,5 +1,5 @@
-"""GPU tuning aid: times the persistent recurrent kernels of one C2-sized BLSTM layer for every sequence-group count G
-(BLSTM_FWD_G / BLSTM_BWD_G override the plan's cost model).  Prints one JSON line per G.
+"""GPU tuning aid: times the persistent recurrent kernels of one BLSTM layer for every feasible (sequence groups G,
+sub-CTAs per CTA) pair; BLSTM_{FWD,BWD}_{G,NSUB} override the plan's cost model.  One JSON line per configuration.
     python tools/sweep_geometry.py [H] [S] [T]"""
 import ctypes
 import json
@@ -27,20 +27,22 @@ ctx = cb.Context(0)
 k, _ = cb.libs()
 ds = cb.DataSet(ctx, xs, S, seq_classes=cs, O=16, training=False)
 frac = ds.next_fraction()
-for G in [0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 12, 13, 15]:
-    os.environ["BLSTM_FWD_G"] = str(G)
-    os.environ["BLSTM_BWD_G"] = str(G)
+
+
+def measure(which, G, nsub):
+    for key in ("BLSTM_FWD_G", "BLSTM_BWD_G", "BLSTM_FWD_NSUB", "BLSTM_BWD_NSUB"):
+        os.environ.pop(key, None)
+    if G:
+        os.environ["BLSTM_%s_G" % which] = str(G)
+        os.environ["BLSTM_%s_NSUB" % which] = str(nsub)
     try:
         net = cb.Net(ctx, net_json, S, T)
-    except RuntimeError as e:
-        print(json.dumps({"G": G, "error": str(e)[:80]}))
-        continue
+    except RuntimeError:
+        return None
     for i, w in enumerate(weights):
         if len(w):
             net.set_weights(i, w)
     info = net.plan_info(1)
-    if G and (info["fwd_G"] != G and info["bwd_G"] != G):
-        continue
     net.load_fraction(frac)
     for it in range(2):
         net.forward(); net.calculate_error(); net.backward()
@@ -52,6 +54,18 @@ for G in [0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 12, 13, 15]:
         net.forward(); net.calculate_error(); net.backward()
     k.bl_ctx_timing_read(ctx.p, ms, cnt)
     k.bl_ctx_timing_enable(ctx.p, 0)
-    print(json.dumps({"G_req": G, "plan": info, "fwd_us_per_step": 1e3 * ms[1] / reps / T, "bwd_us_per_step": 1e3 * ms[2] / reps / T,
-                      "fwd_ms": ms[1] / reps, "bwd_ms": ms[2] / reps}), flush=True)
-    del net
+    idx = 1 if which == "FWD" else 2
+    key = which.lower()
+    return {"which": key, "G": info[key + "_G"], "nsub": info[key + "_nsub"], "C": info[key + "_C"], "CL": info[key + "_CL"],
+            "smem": info[key + "_smem"], "us_per_step": round(1e3 * ms[idx] / reps / T, 3)}
+
+
+for which in ("FWD", "BWD"):
+    r = measure(which, 0, 0)
+    r["default"] = True
+    print(json.dumps(r), flush=True)
+    for nsub in (1, 2, 4):
+        for Gc in range(1, 13):
+            r = measure(which, Gc * nsub, nsub)
+            if r:
+                print(json.dumps(r), flush=True)

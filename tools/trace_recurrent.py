@@ -1,0 +1,43 @@
+"""GPU tuning aid: per-phase cycle breakdown of the forward persistent kernel from in-kernel clock64 stamps.
+    BLSTM_REC_TRACE=1 [BLSTM_FWD_G=.. BLSTM_FWD_NSUB=..] python tools/trace_recurrent.py [H] [S] [T]"""
+import ctypes
+import os
+import sys
+
+import numpy as np
+
+os.environ.setdefault("BLSTM_REC_TRACE", "1")
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path[:0] = [ROOT, os.path.join(ROOT, "lstm-rnn_b200", "python")]
+import currennt_b200 as cb   # noqa: E402
+import synth                 # noqa: E402
+
+H = int(sys.argv[1]) if len(sys.argv) > 1 else 250
+S = int(sys.argv[2]) if len(sys.argv) > 2 else 100
+T = int(sys.argv[3]) if len(sys.argv) > 3 else 300
+P = 64
+net_json = synth.network_json(P, [2 * H], 16)
+xs, cs, _ = synth.make_sequences(np.full(S, T), P, 1, classes=16)
+ctx = cb.Context(0)
+k, h = cb.libs()
+ds = cb.DataSet(ctx, xs, S, seq_classes=cs, O=16, training=False)
+frac = ds.next_fraction()
+net = cb.Net(ctx, net_json, S, T)
+for i, w in enumerate(synth.init_weights(net_json, 2)):
+    if len(w):
+        net.set_weights(i, w)
+print("plan", net.plan_info(1))
+net.load_fraction(frac)
+for it in range(3):
+    net.forward()
+ctx.sync()
+buf = np.zeros((ctx.num_sms * 4, T, 6), np.int64)
+rows = ctypes.c_int()
+h.cn_lstm_debug_trace.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.POINTER(ctypes.c_int)]
+assert h.cn_lstm_debug_trace(net.p, 1, T, buf.ctypes.data_as(ctypes.c_void_p), ctypes.byref(rows)) == 0, h.cn_last_error()
+tr = buf.reshape(-1)[: rows.value * T * 6].reshape(rows.value, T, 6)[:, 5:T - 1, :]      # skip the first steps and the last
+d = {"prefetch+wait": tr[:, :, 1] - tr[:, :, 0], "copy": tr[:, :, 2] - tr[:, :, 1], "gemm": tr[:, :, 3] - tr[:, :, 2],
+     "gate math+stores": tr[:, :, 4] - tr[:, :, 3], "publish": tr[:, :, 5] - tr[:, :, 4], "step": tr[:, 1:, 0] - tr[:, :-1, 0]}
+for name, v in d.items():
+    per_row = v.mean(1)
+    print("%-18s mean %8.0f cyc   min-row %8.0f  max-row %8.0f  p99 %8.0f" % (name, v.mean(), per_row.min(), per_row.max(), np.percentile(v, 99)))
