@@ -113,11 +113,12 @@ int bl_lstm_plan_create(bl_ctx *ctx, int P, int L, int bidirectional, int S, int
     pl->flags_f = pl->flags_b = nullptr;
     pl->trace = nullptr;
 
-    const int cap = ctx->smem_optin - 1024;
+    const int cap = ctx->smem_optin - 2048;      // room for the kernels' static shared memory (exp table) and the driver's reserve
     // tuning overrides (tools/sweep_geometry.py): sequence groups and sub-CTAs per CTA of either kernel
-    const char *ef = getenv("BLSTM_FWD_G"), *eb = getenv("BLSTM_BWD_G"), *nf = getenv("BLSTM_FWD_NSUB"), *nb = getenv("BLSTM_BWD_NSUB");
-    if (!bl::choose_geometry(false, pl->H, S, pl->ndir, ctx->num_sms, cap, ef ? atoi(ef) : 0, nf ? atoi(nf) : 0, &pl->gf) ||
-        !bl::choose_geometry(true, pl->H, S, pl->ndir, ctx->num_sms, cap, eb ? atoi(eb) : 0, nb ? atoi(nb) : 0, &pl->gb)) {
+    const char *ef = getenv("BLSTM_FWD_G"), *eb = getenv("BLSTM_BWD_G"), *nf = getenv("BLSTM_FWD_NSUB"), *nb = getenv("BLSTM_BWD_NSUB"),
+               *tf = getenv("BLSTM_FWD_NT"), *tb = getenv("BLSTM_BWD_NT");
+    if (!bl::choose_geometry(false, pl->H, S, pl->ndir, ctx->num_sms, cap, ef ? atoi(ef) : 0, nf ? atoi(nf) : 0, tf ? atoi(tf) : 0, &pl->gf) ||
+        !bl::choose_geometry(true, pl->H, S, pl->ndir, ctx->num_sms, cap, eb ? atoi(eb) : 0, nb ? atoi(nb) : 0, tb ? atoi(tb) : 0, &pl->gb)) {
         delete pl;
         return bl::fail(ctx, "bl_lstm_plan_create: no persistent-kernel geometry fits (H=%d S=%d): recurrent weights do not fit in shared memory",
                         L / (bidirectional ? 2 : 1), S);

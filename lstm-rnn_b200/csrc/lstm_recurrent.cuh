@@ -4,17 +4,18 @@
 
 namespace bl {
 
-constexpr int REC_NT = 512;            // threads per CTA (16 warps, 1 CTA per SM)
-constexpr int REC_NW = REC_NT / 32;
+constexpr int REC_NT_MAX = 1024;       // threads per CTA: 1024 (64 registers each) or 768 (85 registers), 1 CTA per SM
 constexpr int REC_NPAIR = 2;           // (cell, sequence) pairs per thread in the elementwise phase
 
 // Launch geometry of one persistent kernel.  One CTA owns CL cells of one direction for the SG sequences of
 // one sequence group; its slice of the recurrent weights stays in shared memory for the whole pass.
 struct RecGeom {
     int G, C, CL, SG;       // sequence groups (all sub-CTAs counted), cell slices per (direction, group), cells per CTA, sequences per group
+    int NT;                 // threads per CTA (768 or 1024)
     int nsub;               // sub-CTAs per CTA: each owns one sequence group and has its own barrier and step counter, so one
                             // group's counter wait / exchange copy overlaps the other groups' FFMA work on the same SM; all
                             // sub-CTAs share the CTA's weight slice in shared memory.  CTAs per direction = (G / nsub) * C
+    int npair;              // (cell, sequence) pairs per thread in the gate-math phase: 1 or 2
     int R;                  // GEMM rows per CTA: 4*CL (forward: gate x cell), CL (BPTT: cell)
     int LR, LS, LSlog;      // lanes along row quads / sequence quads (LR*LS == 32)
     int WR, WS, KS;         // warp tiles along rows / sequences, K splits
@@ -28,7 +29,7 @@ struct RecGeom {
     double cost;
 };
 
-bool choose_geometry(bool bwd, int H, int S, int ndir, int num_sms, int smem_cap, int forceG, int forceNsub, RecGeom *out);
+bool choose_geometry(bool bwd, int H, int S, int ndir, int num_sms, int smem_cap, int forceG, int forceNsub, int forceNT, RecGeom *out);
 
 struct RecFwdParams {
     const float *Wb, *Wi, *Wp;      // bias / internal / peephole segments of the layer's weight vector

@@ -29,15 +29,19 @@ ds = cb.DataSet(ctx, xs, S, seq_classes=cs, O=16, training=False)
 frac = ds.next_fraction()
 
 
-def measure(which, G, nsub):
-    for key in ("BLSTM_FWD_G", "BLSTM_BWD_G", "BLSTM_FWD_NSUB", "BLSTM_BWD_NSUB"):
+def measure(which, G, nsub, NT=0):
+    for key in ("BLSTM_FWD_G", "BLSTM_BWD_G", "BLSTM_FWD_NSUB", "BLSTM_BWD_NSUB", "BLSTM_FWD_NT", "BLSTM_BWD_NT"):
         os.environ.pop(key, None)
+    if NT:
+        os.environ["BLSTM_%s_NT" % which] = str(NT)
     if G:
         os.environ["BLSTM_%s_G" % which] = str(G)
         os.environ["BLSTM_%s_NSUB" % which] = str(nsub)
     try:
         net = cb.Net(ctx, net_json, S, T)
-    except RuntimeError:
+    except RuntimeError as e:
+        if not G:
+            print(json.dumps({"error": str(e)[:300]}), flush=True)
         return None
     for i, w in enumerate(weights):
         if len(w):
@@ -56,16 +60,19 @@ def measure(which, G, nsub):
     k.bl_ctx_timing_enable(ctx.p, 0)
     idx = 1 if which == "FWD" else 2
     key = which.lower()
-    return {"which": key, "G": info[key + "_G"], "nsub": info[key + "_nsub"], "C": info[key + "_C"], "CL": info[key + "_CL"],
+    return {"which": key, "NT": NT, "G": info[key + "_G"], "nsub": info[key + "_nsub"], "C": info[key + "_C"], "CL": info[key + "_CL"],
             "smem": info[key + "_smem"], "us_per_step": round(1e3 * ms[idx] / reps / T, 3)}
 
 
 for which in ("FWD", "BWD"):
     r = measure(which, 0, 0)
-    r["default"] = True
-    print(json.dumps(r), flush=True)
-    for nsub in (1, 2, 4):
-        for Gc in range(1, 13):
-            r = measure(which, Gc * nsub, nsub)
-            if r:
-                print(json.dumps(r), flush=True)
+    if r:
+        r["default"] = True
+        print(json.dumps(r), flush=True)
+    seen = set()
+    for NT in (512, 768, 1024):
+        for nsub in (1, 2, 4):
+            for Gc in range(1, 13):
+                r = measure(which, Gc * nsub, nsub, NT)
+                if r and (r["G"], r["nsub"]) == (Gc * nsub, nsub):
+                    print(json.dumps(r), flush=True)
