@@ -62,6 +62,9 @@ const char *bl_last_error(const bl_ctx *ctx);
 int  bl_sync(bl_ctx *ctx);
 /* 0 = strict (default), 1 = fast; applies to the GEMMs issued by the layer-level calls */
 int  bl_ctx_set_gemm_mode(bl_ctx *ctx, int mode);
+/* GEMM backend: 0 = automatic (tcgen05 tensor-core path for large contractions, SIMT FFMA for small ones),
+ * 1 = SIMT only, 2 = tcgen05 always (tests).  The precision mode applies to either backend. */
+int  bl_ctx_set_gemm_backend(bl_ctx *ctx, int backend);
 int  bl_ctx_num_sms(const bl_ctx *ctx);
 /* number of kernels this library has launched on the context since creation (bench.py gpu_launches) */
 long bl_ctx_launch_count(const bl_ctx *ctx);

@@ -1,6 +1,7 @@
 // Context, memory and error plumbing of the C ABI (include/blstm_b200.h).
 #include "common.cuh"
 #include <cstring>
+#include <cstdlib>
 
 namespace bl {
 thread_local std::string g_err;
@@ -81,6 +82,7 @@ int bl_ctx_create(int device, void *stream, bl_ctx **out)
     ctx->num_sms = prop.multiProcessorCount;
     ctx->smem_optin = (int)prop.sharedMemPerBlockOptin;
     ctx->gemm_mode = BL_GEMM_STRICT;
+    { const char *e = getenv("BLSTM_GEMM_BACKEND"); ctx->gemm_backend = e ? atoi(e) : 0; }
     ctx->launches = 0;
     ctx->timing = false;
     ctx->scratch = nullptr;
@@ -114,6 +116,13 @@ int bl_ctx_set_gemm_mode(bl_ctx *ctx, int mode)
 {
     if (mode != BL_GEMM_STRICT && mode != BL_GEMM_FAST) return bl::fail(ctx, "bad gemm mode %d", mode);
     ctx->gemm_mode = mode;
+    return 0;
+}
+
+int bl_ctx_set_gemm_backend(bl_ctx *ctx, int backend)
+{
+    if (backend < 0 || backend > 2) return bl::fail(ctx, "bad gemm backend %d", backend);
+    ctx->gemm_backend = backend;
     return 0;
 }
 

@@ -8,6 +8,9 @@
 
 namespace bl {
 
+int gemm_tf32_tc(bl_ctx *ctx, int M, int N, int K, const float *A, size_t lda, bool a_kmajor, const float *B, size_t ldb, bool b_kmajor,
+                 float *C, int ldc, int accumulate, int mode);
+
 constexpr int BM = 128, BN = 128, BK = 16, GT = 256;
 constexpr int LDS_A = BM + 4, LDS_B = BN + 4;      // +4 floats: keeps 16 B alignment, breaks the store conflicts
 
@@ -190,6 +193,15 @@ extern "C" int bl_gemm_f32(bl_ctx *ctx, int transA, int transB, int m, int n, in
     const int rowsA = transA ? k : m, rowsB = transB ? n : k;
     if (lda < (rowsA > 1 ? rowsA : 1) || ldb < (rowsB > 1 ? rowsB : 1) || ldc < (m > 1 ? m : 1))
         return bl::fail(ctx, "bl_gemm_f32: leading dimension too small (lda=%d ldb=%d ldc=%d)", lda, ldb, ldc);
-    (void)mode;     // strict and fast both map to the SIMT kernel until the tcgen05 path lands for a shape
+    if (transA && transB) return bl::fail(ctx, "gemm: (transA,transB)=(1,1) is not implemented (as in helpers/Matrix.cu:248)");
+    if (mode != BL_GEMM_STRICT && mode != BL_GEMM_FAST) return bl::fail(ctx, "bl_gemm_f32: bad mode %d", mode);
+    // tensor-core path for the large time-parallel contractions; the tiny ones (a few output tiles, short K) stay on FFMA
+    const double macs = (double)m * n * k;
+    const bool big = macs >= 64.0 * 1024 * 1024 && k >= 64 && m >= 32 && n >= 32;
+    if (ctx->gemm_backend == 2 || (ctx->gemm_backend == 0 && big)) {
+        // column-major C[m x n] == row-major C'[n x m] = opB^T[n x k] * (opA^T[m x k])^T
+        return bl::gemm_tf32_tc(ctx, n, m, k, B, (size_t)ldb, /*a_kmajor=*/!transB, A, (size_t)lda, /*b_kmajor=*/transA != 0,
+                                C, ldc, accumulate, mode);
+    }
     return bl::gemm_f32_simt(ctx, transA, transB, m, n, k, A, lda, B, ldb, C, ldc, accumulate);
 }

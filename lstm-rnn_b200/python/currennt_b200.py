@@ -55,6 +55,7 @@ def libs():
         k.bl_sync.argtypes = [vp]
         k.bl_ctx_set_gemm_mode.argtypes = [vp, ci]
         k.bl_ctx_num_sms.argtypes = [vp]
+        k.bl_ctx_set_gemm_backend.argtypes = [vp, ci]
         k.bl_ctx_launch_count.restype = cl
         k.bl_ctx_launch_count.argtypes = [vp]
         k.bl_malloc.argtypes = [vp, ctypes.POINTER(vp), ctypes.c_size_t]
@@ -143,6 +144,9 @@ class Context:
 
     def set_gemm_mode(self, mode):
         self.check(self.k.bl_ctx_set_gemm_mode(self.p, mode))
+
+    def set_gemm_backend(self, backend):
+        self.check(self.k.bl_ctx_set_gemm_backend(self.p, backend))
 
     @property
     def num_sms(self):
