@@ -232,3 +232,66 @@ def test_error_conventions(gpu_ctx):
     net = cb.Net(gpu_ctx, synth.network_json(4, [6], 3), 2, 4)
     with pytest.raises(RuntimeError, match="wrong number of weights"):
         net.set_weights(1, np.zeros(5, np.float32))
+
+
+# ----------------------------------------------------------------------------- tcgen05 tensor-core GEMM
+TC_SHAPES = [
+    # transA, transB, m, n, k, pad   (column-major convention of bl_gemm_f32)
+    (1, 0, 256, 384, 128, 0),          # projection shape class: both operands already K-major
+    (1, 0, 2000, 1000, 500, 0),
+    (1, 0, 2000, 777, 123, 0),         # K-major but lda=123 not 16-byte aligned -> repacked
+    (0, 0, 500, 900, 2000, 0),         # input-error class: A must be transposed
+    (0, 1, 500, 2000, 4100, 0),        # weight-gradient class: both transposed, split-K
+    (0, 1, 250, 250, 3000, 2),
+    (1, 0, 183, 300, 500, 1),
+    (1, 0, 40, 33, 70, 0),             # smaller than one tile
+]
+
+
+@pytest.mark.parametrize("mode,tol", [(0, 3e-6), (1, 2e-3)], ids=["strict3xTF32", "fastTF32"])
+@pytest.mark.parametrize("shape", TC_SHAPES, ids=lambda s: "x".join(map(str, s)))
+def test_tensor_core_gemm(gpu_ctx, shape, mode, tol):
+    """bl_gemm_f32 forced onto the tcgen05 path: strict (3xTF32) stays in the fp32 error class, fast within 2e-3."""
+    tA, tB, m, n, k, pad = shape
+    rng = np.random.default_rng(m + n + k)
+    rowsA, colsA = (k, m) if tA else (m, k)
+    rowsB, colsB = (n, k) if tB else (k, n)
+    lda, ldb, ldc = rowsA + pad, rowsB + pad, m + pad
+    A = rng.standard_normal((colsA, lda)).astype(np.float32)
+    B = rng.standard_normal((colsB, ldb)).astype(np.float32)
+    C0 = rng.standard_normal((n, ldc)).astype(np.float32)
+    Am = A[:, :rowsA].T.astype(np.float64)
+    Bm = B[:, :rowsB].T.astype(np.float64)
+    want = (Am.T if tA else Am) @ (Bm.T if tB else Bm)
+    gpu_ctx.set_gemm_backend(2)
+    try:
+        for accumulate in (0, 1):
+            dA, dB, dC = gpu_ctx.to_device(A), gpu_ctx.to_device(B), gpu_ctx.to_device(C0)
+            gpu_ctx.gemm(tA, tB, m, n, k, dA, lda, dB, ldb, dC, ldc, accumulate, mode)
+            C = gpu_ctx.to_host(dC, (n, ldc))
+            for p in (dA, dB, dC):
+                gpu_ctx.free(p)
+            ref = want + C0[:, :m].T if accumulate else want
+            err = rel_err(C[:, :m].T, ref)
+            assert err <= tol, (shape, mode, accumulate, err)
+            if pad:
+                assert np.array_equal(C[:, m:], C0[:, m:])
+    finally:
+        gpu_ctx.set_gemm_backend(0)
+
+
+def test_network_parity_with_tensor_core_gemms(oracle, gpu_ctx):
+    """Whole-network parity with every GEMM forced through the tcgen05 path: strict mode keeps the 1e-5 bar,
+    fast mode the 2e-3 bar of the optional TF32 projection mode (BASELINE.json north_star)."""
+    net_json = synth.network_json(41, [128, 96], 33)
+    lengths = [5, 7, 9, 9, 10, 12, 12, 12, 13, 13, 14, 14, 16, 16, 17, 20]
+    gpu_ctx.set_gemm_backend(2)
+    try:
+        worst = check_net(oracle, gpu_ctx, net_json, 16, lengths, 33, 0, seed=9)
+        print("strict tcgen05 worst rel err %.2e" % worst)
+        gpu_ctx.set_gemm_mode(1)
+        worst = check_net(oracle, gpu_ctx, net_json, 16, lengths, 33, 0, seed=9, tol=2e-3)
+        print("fast tcgen05 worst rel err %.2e" % worst)
+    finally:
+        gpu_ctx.set_gemm_mode(0)
+        gpu_ctx.set_gemm_backend(0)
