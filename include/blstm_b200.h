@@ -60,7 +60,8 @@ int  bl_ctx_create(int device, void *stream, bl_ctx **out);
 void bl_ctx_destroy(bl_ctx *ctx);
 const char *bl_last_error(const bl_ctx *ctx);
 int  bl_sync(bl_ctx *ctx);
-/* 0 = strict (default), 1 = fast; applies to the GEMMs issued by the layer-level calls */
+/* 0 = strict (default), 1 = fast; applies to the forward projections issued by the layer-level calls
+ * (W^T X of the LSTM / feed-forward layers); the backward contractions always run strict */
 int  bl_ctx_set_gemm_mode(bl_ctx *ctx, int mode);
 /* GEMM backend: 0 = automatic (tcgen05 tensor-core path for large contractions, SIMT FFMA for small ones),
  * 1 = SIMT only, 2 = tcgen05 always (tests).  The precision mode applies to either backend. */

@@ -286,9 +286,9 @@ int bl_ff_backward(bl_ctx *ctx, int act, int P, int O, int N, float bias, const 
     if (act != BL_ACT_IDENTITY) BL_LAUNCHED(ctx);
     }
     // plErrorsMatrix.assignProduct(weightsMatrix, false, deltasMatrix, false), FeedForwardLayer.cu:190-197
-    if (dX) BL_CHECK(bl_gemm_f32(ctx, 0, 0, P, N, O, W, P, dY, lddy, dX, lddx, 0, ctx->gemm_mode));
+    if (dX) BL_CHECK(bl_gemm_f32(ctx, 0, 0, P, N, O, W, P, dY, lddy, dX, lddx, 0, BL_GEMM_STRICT));
     // weightUpdatesMatrix.assignProduct(plOutputsMatrix, false, deltasMatrix, true), :200-207
-    BL_CHECK(bl_gemm_f32(ctx, 0, 1, P, O, N, X, ldx, dY, lddy, dW, P, 0, ctx->gemm_mode));
+    BL_CHECK(bl_gemm_f32(ctx, 0, 1, P, O, N, X, ldx, dY, lddy, dW, P, 0, BL_GEMM_STRICT));
     // bias weight updates, :210-223
     int nsplit = 64, rows = cdiv(N, nsplit);
     if (rows < 64) rows = 64;

@@ -208,10 +208,11 @@ int bl_lstm_backward(bl_lstm_plan *pl, const float *W, const float *X, int ldx, 
     BL_CHECK(bl::launch_lstm_bwd(ctx, p));
 
     // (2) error to the preceding layer: dX[P x N] = Win[P x 4L] * deltas[4L x N]   (the 8 products of :996-1006)
-    if (dX) BL_CHECK(bl_gemm_f32(ctx, 0, 0, P, N, 4 * L, W, P, pl->deltas, 4 * L, dX, lddx, 0, ctx->gemm_mode));
+    // (the optional fast mode only relaxes the forward projections; gradients always use the strict path)
+    if (dX) BL_CHECK(bl_gemm_f32(ctx, 0, 0, P, N, 4 * L, W, P, pl->deltas, 4 * L, dX, lddx, 0, BL_GEMM_STRICT));
 
     // (3) input weight gradients: dWin[P x 4L] = X[P x N] * deltas^T   (ComputeWeightUpdateFn case 0x0, :372-389)
-    BL_CHECK(bl_gemm_f32(ctx, 0, 1, P, 4 * L, N, X, ldx, pl->deltas, 4 * L, dW, P, 0, ctx->gemm_mode));
+    BL_CHECK(bl_gemm_f32(ctx, 0, 1, P, 4 * L, N, X, ldx, pl->deltas, 4 * L, dW, P, 0, BL_GEMM_STRICT));
 
     // (4) recurrent weight gradients, one [H x H] block per (gate, direction) (case 0x8, :411-437, 493-500):
     //     fw: dW[k,j] = sum_{n>=S}  h[n-S,k] * delta[n,j];   bw: dW[k,j] = sum_{n<N-S} h[n+S,k] * delta[n,j]
@@ -222,7 +223,7 @@ int bl_lstm_backward(bl_lstm_plan *pl, const float *W, const float *X, int ldx, 
             if (N - S > 0) {
                 const float *A = (d == 0) ? Y : Y + (size_t)S * ldy + H;
                 const float *B = (d == 0) ? pl->deltas + (size_t)S * 4 * L + col : pl->deltas + col;
-                BL_CHECK(bl_gemm_f32(ctx, 0, 1, H, H, N - S, A, ldy, B, 4 * L, blk, H, 0, ctx->gemm_mode));
+                BL_CHECK(bl_gemm_f32(ctx, 0, 1, H, H, N - S, A, ldy, B, 4 * L, blk, H, 0, BL_GEMM_STRICT));
             } else {
                 BL_CHECK(bl_memset(ctx, blk, 0, (size_t)H * H * sizeof(float)));
             }
