@@ -40,6 +40,15 @@ TimedRegion::~TimedRegion()
 {
     if (on) { cudaEventRecord(b, ctx->stream); ctx->tev[cls].emplace_back(a, b); }
 }
+int ensure_scratch2(bl_ctx *ctx, size_t bytes)
+{
+    if (bytes <= ctx->scratch2_bytes) return 0;
+    if (ctx->scratch2) { BL_CUDA(ctx, cudaStreamSynchronize(ctx->stream)); BL_CUDA(ctx, cudaFree(ctx->scratch2)); ctx->scratch2 = nullptr; ctx->scratch2_bytes = 0; }
+    size_t want = bytes + bytes / 4;
+    BL_CUDA(ctx, cudaMalloc(&ctx->scratch2, want));
+    ctx->scratch2_bytes = want;
+    return 0;
+}
 } // namespace bl
 
 extern "C" {
@@ -87,6 +96,8 @@ int bl_ctx_create(int device, void *stream, bl_ctx **out)
     ctx->timing = false;
     ctx->scratch = nullptr;
     ctx->scratch_bytes = 0;
+    ctx->scratch2 = nullptr;
+    ctx->scratch2_bytes = 0;
     if (stream) { ctx->stream = (cudaStream_t)stream; ctx->own_stream = false; }
     else {
         if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess) {
@@ -104,6 +115,7 @@ void bl_ctx_destroy(bl_ctx *ctx)
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     if (ctx->scratch) cudaFree(ctx->scratch);
+    if (ctx->scratch2) cudaFree(ctx->scratch2);
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }

@@ -5,11 +5,9 @@
 // split-K (partials + ordered reduce) for the weight-gradient shapes (tiny m x n, k = T*S).
 // Used for every contraction in strict mode until the tcgen05 path takes the aligned TN shapes.
 #include "common.cuh"
+#include "gemm_tc.cuh"
 
 namespace bl {
-
-int gemm_tf32_tc(bl_ctx *ctx, int M, int N, int K, const float *A, size_t lda, bool a_kmajor, const float *B, size_t ldb, bool b_kmajor,
-                 float *C, int ldc, int accumulate, int mode);
 
 constexpr int BM = 128, BN = 128, BK = 16, GT = 256;
 constexpr int LDS_A = BM + 4, LDS_B = BN + 4;      // +4 floats: keeps 16 B alignment, breaks the store conflicts
@@ -137,6 +135,13 @@ __global__ void splitk_reduce_kernel(int m, int n, int nsplit, const float *__re
     }
 }
 
+bool tc_wanted(const bl_ctx *ctx, int m, int n, int k)
+{
+    const double macs = (double)m * n * k;
+    const bool big = macs >= 64.0 * 1024 * 1024 && k >= 64 && m >= 32 && n >= 32;
+    return ctx->gemm_backend == 2 || (ctx->gemm_backend == 0 && big);
+}
+
 int gemm_f32_simt(bl_ctx *ctx, int transA, int transB, int m, int n, int k,
                   const float *A, int lda, const float *B, int ldb, float *C, int ldc, int accumulate)
 {
@@ -196,9 +201,7 @@ extern "C" int bl_gemm_f32(bl_ctx *ctx, int transA, int transB, int m, int n, in
     if (transA && transB) return bl::fail(ctx, "gemm: (transA,transB)=(1,1) is not implemented (as in helpers/Matrix.cu:248)");
     if (mode != BL_GEMM_STRICT && mode != BL_GEMM_FAST) return bl::fail(ctx, "bl_gemm_f32: bad mode %d", mode);
     // tensor-core path for the large time-parallel contractions; the tiny ones (a few output tiles, short K) stay on FFMA
-    const double macs = (double)m * n * k;
-    const bool big = macs >= 64.0 * 1024 * 1024 && k >= 64 && m >= 32 && n >= 32;
-    if (ctx->gemm_backend == 2 || (ctx->gemm_backend == 0 && big)) {
+    if (bl::tc_wanted(ctx, m, n, k)) {
         // column-major C[m x n] == row-major C'[n x m] = opB^T[n x k] * (opA^T[m x k])^T
         return bl::gemm_tf32_tc(ctx, n, m, k, B, (size_t)ldb, /*a_kmajor=*/!transB, A, (size_t)lda, /*b_kmajor=*/transA != 0,
                                 C, ldc, accumulate, mode);

@@ -15,13 +15,11 @@
 // Operands that are not K-major / 16-byte aligned are first transposed into scratch (bandwidth-bound pass).
 // Split-K (grid.z) with ordered partial-sum reduction keeps the result deterministic.
 #include "common.cuh"
+#include "gemm_tc.cuh"
 #include <cuda.h>
 #include <cstdint>
 
 namespace bl {
-
-int gemm_f32_simt(bl_ctx *ctx, int transA, int transB, int m, int n, int k,
-                  const float *A, int lda, const float *B, int ldb, float *C, int ldc, int accumulate);
 
 constexpr int TC_BM = 128, TC_BK = 32, TC_UMMA_K = 8, TC_THREADS = 256;
 
@@ -29,6 +27,7 @@ struct GemmTcParams {
     CUtensorMap tmA, tmAlo, tmB, tmBlo;     // lo maps unused in fast mode
     float *C; int ldc;
     int M, N, K;
+    int a_k0, b_k0;                          // element offsets added to the K coordinate of the A / B boxes (time-shifted operands)
     int kblocks_per_split;
     int accumulate;
     float *partial; int ldp;                 // split-K: slice z at partial + z*M*ldp
@@ -167,11 +166,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tf32_tcgen05_kernel(const 
                 uint8_t *st = smem + s * STAGE_BYTES;
                 mbar_expect_tx(&full[s], STAGE_BYTES);
                 const int kc = (kb_begin + i) * TC_BK;
-                tma_load_2d(st, &p.tmA, &full[s], kc, m0);
-                tma_load_2d(st + A_BYTES, &p.tmB, &full[s], kc, n0);
+                tma_load_2d(st, &p.tmA, &full[s], kc + p.a_k0, m0);
+                tma_load_2d(st + A_BYTES, &p.tmB, &full[s], kc + p.b_k0, n0);
                 if (STRICT) {
-                    tma_load_2d(st + A_BYTES + B_BYTES, &p.tmAlo, &full[s], kc, m0);
-                    tma_load_2d(st + 2 * A_BYTES + B_BYTES, &p.tmBlo, &full[s], kc, n0);
+                    tma_load_2d(st + A_BYTES + B_BYTES, &p.tmAlo, &full[s], kc + p.a_k0, m0);
+                    tma_load_2d(st + 2 * A_BYTES + B_BYTES, &p.tmBlo, &full[s], kc + p.b_k0, n0);
                 }
             }
         }
@@ -250,36 +249,57 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tf32_tcgen05_kernel(const 
     }
 }
 
-// ------------------------------------------------------------------------------------------------ helper kernels
-// dst[c][r] (ldd) = src[r][c] (lds): 32x32 tiles through shared memory, both sides coalesced
-__global__ void transpose_kernel(int R, int Cc, const float *__restrict__ src, size_t lds, float *__restrict__ dst, size_t ldd)
+// ------------------------------------------------------------------------------------------------ operand preparation
+// One fused, bandwidth-bound pass per operand: bring it into K-major [rows][ld] form (transposing if needed) and, in strict
+// mode, split it into hi = tf32_rna(x) (low 13 mantissa bits zero) and lo = x - hi (exact in fp32).
+__device__ __forceinline__ void split_tf32(float v, float &hi, float &lo)
+{
+    uint32_t h;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h) : "f"(v));
+    hi = __uint_as_float(h);
+    lo = __fsub_rn(v, hi);
+}
+
+// src [rows][K] (lds) -> hi/lo [rows][ldd]; grid (rows, ceil(ldd/512)), 128 threads x 4 consecutive k
+template <bool STRICT>
+__global__ void prep_rows_kernel(int K, const float *__restrict__ src, size_t lds, float *__restrict__ hi, float *__restrict__ lo, size_t ldd)
+{
+    const size_t r = blockIdx.x;
+    const int k = (blockIdx.y * blockDim.x + threadIdx.x) * 4;
+    if ((size_t)k >= ldd) return;
+    const float *s = src + r * lds + k;
+    float v[4], h[4], l[4];
+    const bool vec = ((lds & 3) == 0) && ((reinterpret_cast<uintptr_t>(src) & 15) == 0) && (k + 4 <= K);
+    if (vec) { const float4 q = *reinterpret_cast<const float4 *>(s); v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w; }
+    else {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) v[i] = (k + i < K) ? s[i] : 0.0f;
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { if (STRICT) split_tf32(v[i], h[i], l[i]); else { h[i] = v[i]; l[i] = 0.0f; } }
+    *reinterpret_cast<float4 *>(hi + r * ldd + k) = make_float4(h[0], h[1], h[2], h[3]);
+    if (STRICT) *reinterpret_cast<float4 *>(lo + r * ldd + k) = make_float4(l[0], l[1], l[2], l[3]);
+}
+
+// src [K][rows] (lds) -> hi/lo [rows][ldd]: 32x32 tiles through shared memory, both sides coalesced
+template <bool STRICT>
+__global__ void prep_transpose_kernel(int K, int rows, const float *__restrict__ src, size_t lds, float *__restrict__ hi,
+                                      float *__restrict__ lo, size_t ldd)
 {
     __shared__ float t[32][33];
-    const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+    const int r0 = blockIdx.x * 32, k0 = blockIdx.y * 32;
     for (int i = threadIdx.y; i < 32; i += 8) {
-        const int r = r0 + i, c = c0 + threadIdx.x;
-        t[i][threadIdx.x] = (r < R && c < Cc) ? src[(size_t)r * lds + c] : 0.0f;
+        const int k = k0 + i, r = r0 + threadIdx.x;
+        t[i][threadIdx.x] = (k < K && r < rows) ? src[(size_t)k * lds + r] : 0.0f;
     }
     __syncthreads();
     for (int i = threadIdx.y; i < 32; i += 8) {
-        const int c = c0 + i, r = r0 + threadIdx.x;
-        if (c < Cc && r < R) dst[(size_t)c * ldd + r] = t[threadIdx.x][i];
-    }
-}
-
-// hi = tf32_rna(x) (low 13 mantissa bits zero), lo = x - hi (exact in fp32); rows x cols with leading dimensions
-__global__ void split_tf32_kernel(int rows, int cols, const float *__restrict__ x, size_t ldx, float *__restrict__ hi,
-                                  float *__restrict__ lo, size_t ldo)
-{
-    const size_t total = (size_t)rows * cols;
-    for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
-        const size_t r = e / cols, c = e % cols;
-        const float v = x[r * ldx + c];
-        uint32_t h;
-        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h) : "f"(v));
-        const float hf = __uint_as_float(h);
-        hi[r * ldo + c] = hf;
-        lo[r * ldo + c] = __fsub_rn(v, hf);
+        const int r = r0 + i, k = k0 + threadIdx.x;
+        if (r < rows && k < K) {
+            const float v = t[threadIdx.x][i];
+            if (STRICT) { float h, l; split_tf32(v, h, l); hi[(size_t)r * ldd + k] = h; lo[(size_t)r * ldd + k] = l; }
+            else hi[(size_t)r * ldd + k] = v;
+        }
     }
 }
 
@@ -332,8 +352,6 @@ static int make_map(bl_ctx *ctx, CUtensorMap *map, const float *base, int rows, 
     return 0;
 }
 
-static inline size_t round4(size_t x) { return (x + 3) & ~(size_t)3; }
-
 template <int BN, bool STRICT, int STAGES>
 static int launch_tc(bl_ctx *ctx, const GemmTcParams &p, dim3 grid)
 {
@@ -346,18 +364,40 @@ static int launch_tc(bl_ctx *ctx, const GemmTcParams &p, dim3 grid)
     return 0;
 }
 
-// C[M x N] row-major (ldc) (+)= A[M x K] * B[N x K]^T.  a_kmajor: A is given as [M][K] (lda) else as [K][M] (lda); same for B.
-int gemm_tf32_tc(bl_ctx *ctx, int M, int N, int K, const float *A, size_t lda, bool a_kmajor, const float *B, size_t ldb, bool b_kmajor,
-                 float *C, int ldc, int accumulate, int mode)
+size_t tc_operand_ld(int K) { return ((size_t)K + 3) & ~(size_t)3; }
+
+// Fills `out` with a K-major view of src ([rows][K] if kmajor else [K][rows], leading dimension ld_src).  hi/lo are caller-owned
+// buffers of rows*tc_operand_ld(K) floats (lo unused in fast mode).  In fast mode an already aligned K-major source is used in place.
+int tc_prepare(bl_ctx *ctx, const float *src, int rows, int K, size_t ld_src, bool kmajor, bool strict, float *hi, float *lo, TcOperand *out)
 {
     TimedRegion timed(ctx, 0);
-    const bool strict = (mode == BL_GEMM_STRICT);
-    const size_t ldk = round4((size_t)K);
-    // scratch layout: [A^T | A_hi | A_lo | B^T | B_hi | B_lo | split-K partials]
-    const bool a_tr = !a_kmajor || (lda & 3) || (reinterpret_cast<uintptr_t>(A) & 15);
-    const bool b_tr = !b_kmajor || (ldb & 3) || (reinterpret_cast<uintptr_t>(B) & 15);
-    const size_t a_elems = (size_t)M * ldk, b_elems = (size_t)N * ldk;
+    out->rows = rows; out->K = K; out->strict = strict;
+    const bool aligned = kmajor && ((ld_src & 3) == 0) && ((reinterpret_cast<uintptr_t>(src) & 15) == 0);
+    if (!strict && aligned) { out->hi = src; out->lo = nullptr; out->ld = ld_src; return 0; }
+    const size_t ldd = tc_operand_ld(K);
+    if (kmajor) {
+        dim3 grid(rows, cdiv((int)ldd, 512));
+        if (strict) prep_rows_kernel<true><<<grid, 128, 0, ctx->stream>>>(K, src, ld_src, hi, lo, ldd);
+        else        prep_rows_kernel<false><<<grid, 128, 0, ctx->stream>>>(K, src, ld_src, hi, lo, ldd);
+    } else {
+        dim3 grid(cdiv(rows, 32), cdiv(K, 32));
+        if (grid.y > 65535) return fail(ctx, "tc_prepare: K too large for the transpose grid");
+        if (strict) prep_transpose_kernel<true><<<grid, dim3(32, 8), 0, ctx->stream>>>(K, rows, src, ld_src, hi, lo, ldd);
+        else        prep_transpose_kernel<false><<<grid, dim3(32, 8), 0, ctx->stream>>>(K, rows, src, ld_src, hi, lo, ldd);
+    }
+    BL_LAUNCHED(ctx);
+    out->hi = hi; out->lo = strict ? lo : nullptr; out->ld = ldd;
+    return 0;
+}
 
+// C[M x N] row-major (ldc) (+)= A[a_row0 .. +M][a_k0 .. +K] * B[b_row0 .. +N][b_k0 .. +K]^T on prepared operands
+int tc_gemm(bl_ctx *ctx, int M, int N, int K, const TcOperand &A, int a_row0, int a_k0, const TcOperand &B, int b_row0, int b_k0,
+            float *C, int ldc, int accumulate)
+{
+    TimedRegion timed(ctx, 0);
+    const bool strict = A.strict;
+    if (A.strict != B.strict) return fail(ctx, "tc_gemm: operands prepared for different precision modes");
+    if (a_row0 + M > A.rows || b_row0 + N > B.rows || a_k0 + K > A.K || b_k0 + K > B.K) return fail(ctx, "tc_gemm: sub-view out of range");
     constexpr int BN_STRICT = 128, BN_FAST = 256;
     const int BN = strict ? BN_STRICT : BN_FAST;
     const int tiles = cdiv(M, TC_BM) * cdiv(N, BN);
@@ -371,59 +411,48 @@ int gemm_tf32_tc(bl_ctx *ctx, int M, int N, int K, const float *A, size_t lda, b
     }
     const int kbs = cdiv(kb_total, nsplit);
     nsplit = cdiv(kb_total, kbs);
-    const size_t ldp = round4((size_t)N);
-    const size_t part_elems = nsplit > 1 ? (size_t)nsplit * M * ldp : 0;
-
-    size_t need = 0;
-    const size_t offAt = need; need += a_tr ? a_elems : 0;
-    const size_t offAh = need; need += strict ? a_elems : 0;
-    const size_t offAl = need; need += strict ? a_elems : 0;
-    const size_t offBt = need; need += b_tr ? b_elems : 0;
-    const size_t offBh = need; need += strict ? b_elems : 0;
-    const size_t offBl = need; need += strict ? b_elems : 0;
-    const size_t offP = need; need += part_elems;
-    BL_CHECK(ensure_scratch(ctx, need * sizeof(float) + 64));
-    float *S = reinterpret_cast<float *>((reinterpret_cast<uintptr_t>(ctx->scratch) + 15) & ~(uintptr_t)15);
-
-    const float *Ak = A; size_t ldak = lda;
-    if (a_tr) {
-        if (a_kmajor) BL_CUDA(ctx, cudaMemcpy2DAsync(S + offAt, ldk * 4, A, lda * 4, (size_t)K * 4, M, cudaMemcpyDeviceToDevice, ctx->stream));
-        else { transpose_kernel<<<dim3(cdiv(M, 32), cdiv(K, 32)), dim3(32, 8), 0, ctx->stream>>>(K, M, A, lda, S + offAt, ldk); BL_LAUNCHED(ctx); }
-        Ak = S + offAt; ldak = ldk;
-    }
-    const float *Bk = B; size_t ldbk = ldb;
-    if (b_tr) {
-        if (b_kmajor) BL_CUDA(ctx, cudaMemcpy2DAsync(S + offBt, ldk * 4, B, ldb * 4, (size_t)K * 4, N, cudaMemcpyDeviceToDevice, ctx->stream));
-        else { transpose_kernel<<<dim3(cdiv(N, 32), cdiv(K, 32)), dim3(32, 8), 0, ctx->stream>>>(K, N, B, ldb, S + offBt, ldk); BL_LAUNCHED(ctx); }
-        Bk = S + offBt; ldbk = ldk;
-    }
+    const size_t ldp = tc_operand_ld(N);
     GemmTcParams p;
-    if (strict) {
-        int blocks = (int)cdivz((size_t)M * K, 256); if (blocks > ctx->num_sms * 16) blocks = ctx->num_sms * 16;
-        split_tf32_kernel<<<blocks, 256, 0, ctx->stream>>>(M, K, Ak, ldak, S + offAh, S + offAl, ldk); BL_LAUNCHED(ctx);
-        blocks = (int)cdivz((size_t)N * K, 256); if (blocks > ctx->num_sms * 16) blocks = ctx->num_sms * 16;
-        split_tf32_kernel<<<blocks, 256, 0, ctx->stream>>>(N, K, Bk, ldbk, S + offBh, S + offBl, ldk); BL_LAUNCHED(ctx);
-        BL_CHECK(make_map(ctx, &p.tmA, S + offAh, M, K, ldk, TC_BM));
-        BL_CHECK(make_map(ctx, &p.tmAlo, S + offAl, M, K, ldk, TC_BM));
-        BL_CHECK(make_map(ctx, &p.tmB, S + offBh, N, K, ldk, BN));
-        BL_CHECK(make_map(ctx, &p.tmBlo, S + offBl, N, K, ldk, BN));
-    } else {
-        BL_CHECK(make_map(ctx, &p.tmA, Ak, M, K, ldak, TC_BM));
-        BL_CHECK(make_map(ctx, &p.tmB, Bk, N, K, ldbk, BN));
-        p.tmAlo = p.tmA; p.tmBlo = p.tmB;
+    p.partial = nullptr;
+    if (nsplit > 1) {
+        BL_CHECK(ensure_scratch2(ctx, (size_t)nsplit * M * ldp * sizeof(float) + 64));
+        p.partial = reinterpret_cast<float *>((reinterpret_cast<uintptr_t>(ctx->scratch2) + 15) & ~(uintptr_t)15);
     }
-    p.C = C; p.ldc = ldc; p.M = M; p.N = N; p.K = K; p.kblocks_per_split = kbs; p.accumulate = accumulate;
-    p.partial = nsplit > 1 ? S + offP : nullptr; p.ldp = (int)ldp;
+    // the maps cover rows [row0, row0+M) and K extent [0, k0+K): boxes running past either edge are zero-filled
+    BL_CHECK(make_map(ctx, &p.tmA, A.hi + (size_t)a_row0 * A.ld, M, a_k0 + K, A.ld, TC_BM));
+    BL_CHECK(make_map(ctx, &p.tmB, B.hi + (size_t)b_row0 * B.ld, N, b_k0 + K, B.ld, BN));
+    if (strict) {
+        BL_CHECK(make_map(ctx, &p.tmAlo, A.lo + (size_t)a_row0 * A.ld, M, a_k0 + K, A.ld, TC_BM));
+        BL_CHECK(make_map(ctx, &p.tmBlo, B.lo + (size_t)b_row0 * B.ld, N, b_k0 + K, B.ld, BN));
+    } else { p.tmAlo = p.tmA; p.tmBlo = p.tmB; }
+    p.C = C; p.ldc = ldc; p.M = M; p.N = N; p.K = K; p.a_k0 = a_k0; p.b_k0 = b_k0;
+    p.kblocks_per_split = kbs; p.accumulate = accumulate; p.ldp = (int)ldp;
     dim3 grid(cdiv(N, BN), cdiv(M, TC_BM), nsplit);
-    if (grid.y > 65535) return fail(ctx, "gemm_tc: M too large");
+    if (grid.y > 65535) return fail(ctx, "tc_gemm: M too large");
     if (strict) BL_CHECK((launch_tc<BN_STRICT, true, 3>(ctx, p, grid)));
     else        BL_CHECK((launch_tc<BN_FAST, false, 4>(ctx, p, grid)));
     if (nsplit > 1) {
         int blocks = (int)cdivz((size_t)M * N, 256); if (blocks > 2048) blocks = 2048;
-        sum_slices_kernel<<<blocks, 256, 0, ctx->stream>>>(M, N, nsplit, S + offP, (int)ldp, C, ldc, accumulate);
+        sum_slices_kernel<<<blocks, 256, 0, ctx->stream>>>(M, N, nsplit, p.partial, (int)ldp, C, ldc, accumulate);
         BL_LAUNCHED(ctx);
     }
     return 0;
+}
+
+// Generic entry used by bl_gemm_f32: prepares both operands in the context's scratch, then multiplies.
+// C[M x N] row-major (ldc) (+)= A[M x K] * B[N x K]^T.  a_kmajor: A is given as [M][K] (lda) else as [K][M] (lda); same for B.
+int gemm_tf32_tc(bl_ctx *ctx, int M, int N, int K, const float *A, size_t lda, bool a_kmajor, const float *B, size_t ldb, bool b_kmajor,
+                 float *C, int ldc, int accumulate, int mode)
+{
+    const bool strict = (mode == BL_GEMM_STRICT);
+    const size_t ldk = tc_operand_ld(K);
+    const size_t a_elems = (size_t)M * ldk, b_elems = (size_t)N * ldk;
+    BL_CHECK(ensure_scratch(ctx, 2 * (a_elems + b_elems) * sizeof(float) + 64));
+    float *S = reinterpret_cast<float *>((reinterpret_cast<uintptr_t>(ctx->scratch) + 15) & ~(uintptr_t)15);
+    TcOperand a, b;
+    BL_CHECK(tc_prepare(ctx, A, M, K, lda, a_kmajor, strict, S, S + a_elems, &a));
+    BL_CHECK(tc_prepare(ctx, B, N, K, ldb, b_kmajor, strict, S + 2 * a_elems, S + 2 * a_elems + b_elems, &b));
+    return tc_gemm(ctx, M, N, K, a, 0, 0, b, 0, 0, C, ldc, accumulate);
 }
 
 } // namespace bl

@@ -12,6 +12,7 @@
 // The layer output Y [N][L] is written directly by the recurrent kernel (no ResortOutputsFn pass, :140-161),
 // and the output errors dY [N][L] are read directly (no ResortOutputErrorsFn pass, :163-188).
 #include "lstm_recurrent.cuh"
+#include "gemm_tc.cuh"
 #include <cstdlib>
 
 namespace bl {
@@ -26,6 +27,8 @@ struct bl_lstm_plan {
     bl::RecGeom gf, gb;
     float *acts, *deltas, *cst, *cerr, *hx, *dx, *gpart;
     long long *trace;
+    float *tcbuf;            // prepared tensor-core operands of the backward pass (hi/lo of deltas, deltas^T, X^T, Y^T, Win^T)
+    size_t tcbuf_elems;
     unsigned *flags_f, *flags_b;
     int gsplit;
     int lastT;
@@ -112,6 +115,7 @@ int bl_lstm_plan_create(bl_ctx *ctx, int P, int L, int bidirectional, int S, int
     pl->acts = pl->deltas = pl->cst = pl->cerr = pl->hx = pl->dx = pl->gpart = nullptr;
     pl->flags_f = pl->flags_b = nullptr;
     pl->trace = nullptr;
+    pl->tcbuf = nullptr; pl->tcbuf_elems = 0;
 
     const int cap = ctx->smem_optin - 2048;      // room for the kernels' static shared memory (exp table) and the driver's reserve
     // tuning overrides (tools/sweep_geometry.py): sequence groups and sub-CTAs per CTA of either kernel
@@ -155,7 +159,7 @@ void bl_lstm_plan_destroy(bl_lstm_plan *pl)
 {
     if (!pl) return;
     cudaStreamSynchronize(pl->ctx->stream);
-    void *bufs[] = { pl->acts, pl->deltas, pl->cst, pl->cerr, pl->hx, pl->dx, pl->gpart, pl->flags_f, pl->flags_b, pl->trace };
+    void *bufs[] = { pl->acts, pl->deltas, pl->cst, pl->cerr, pl->hx, pl->dx, pl->gpart, pl->flags_f, pl->flags_b, pl->trace, pl->tcbuf };
     for (void *b : bufs) if (b) cudaFree(b);
     delete pl;
 }
@@ -207,27 +211,70 @@ int bl_lstm_backward(bl_lstm_plan *pl, const float *W, const float *X, int ldx, 
     p.T = T; p.Tmin = Tmin; p.S = S; p.H = H; p.L = L; p.ndir = pl->ndir; p.g = pl->gb;
     BL_CHECK(bl::launch_lstm_bwd(ctx, p));
 
-    // (2) error to the preceding layer: dX[P x N] = Win[P x 4L] * deltas[4L x N]   (the 8 products of :996-1006)
-    // (the optional fast mode only relaxes the forward projections; gradients always use the strict path)
-    if (dX) BL_CHECK(bl_gemm_f32(ctx, 0, 0, P, N, 4 * L, W, P, pl->deltas, 4 * L, dX, lddx, 0, BL_GEMM_STRICT));
-
-    // (3) input weight gradients: dWin[P x 4L] = X[P x N] * deltas^T   (ComputeWeightUpdateFn case 0x0, :372-389)
-    BL_CHECK(bl_gemm_f32(ctx, 0, 1, P, 4 * L, N, X, ldx, pl->deltas, 4 * L, dW, P, 0, BL_GEMM_STRICT));
-
-    // (4) recurrent weight gradients, one [H x H] block per (gate, direction) (case 0x8, :411-437, 493-500):
-    //     fw: dW[k,j] = sum_{n>=S}  h[n-S,k] * delta[n,j];   bw: dW[k,j] = sum_{n<N-S} h[n+S,k] * delta[n,j]
-    for (int g = 0; g < 4; ++g)
-        for (int d = 0; d < pl->ndir; ++d) {
-            float *blk = dWint + (size_t)g * L * H + (size_t)d * H * H;
-            const int col = g * L + d * H;
-            if (N - S > 0) {
-                const float *A = (d == 0) ? Y : Y + (size_t)S * ldy + H;
-                const float *B = (d == 0) ? pl->deltas + (size_t)S * 4 * L + col : pl->deltas + col;
-                BL_CHECK(bl_gemm_f32(ctx, 0, 1, H, H, N - S, A, ldy, B, 4 * L, blk, H, 0, BL_GEMM_STRICT));
-            } else {
-                BL_CHECK(bl_memset(ctx, blk, 0, (size_t)H * H * sizeof(float)));
-            }
+    if (bl::tc_wanted(ctx, P, 4 * L, N)) {
+        // ---- tensor-core path: every operand is brought into K-major hi/lo form ONCE per layer and reused:
+        //   D  = deltas   [N][4L]      (K = 4L)  -> input error
+        //   DT = deltas^T [4L][N]      (K = N)   -> input-weight gradient and all 8 recurrent-weight gradient blocks (row sub-views)
+        //   XT = X^T      [P][N], YT = Y^T [L][N] (K = N), WT = Win^T [P][4L] (K = 4L)
+        const bool strict = true;            // gradients always use the strict (3xTF32) mode
+        const size_t ldN = bl::tc_operand_ld(N), ld4L = bl::tc_operand_ld(4 * L);
+        const size_t maxN = (size_t)pl->maxT * S, ldNmax = bl::tc_operand_ld((int)maxN);
+        const size_t eD = maxN * ld4L, eDT = (size_t)4 * L * ldNmax, eXT = (size_t)P * ldNmax, eYT = (size_t)L * ldNmax, eWT = (size_t)P * ld4L;
+        const size_t need = 2 * (eD + eDT + eXT + eYT + eWT) + 16;
+        if (pl->tcbuf_elems < need) {
+            if (pl->tcbuf) { BL_CUDA(ctx, cudaStreamSynchronize(ctx->stream)); BL_CUDA(ctx, cudaFree(pl->tcbuf)); pl->tcbuf = nullptr; }
+            BL_CUDA(ctx, cudaMalloc(&pl->tcbuf, need * sizeof(float)));
+            pl->tcbuf_elems = need;
         }
+        float *b = pl->tcbuf;
+        float *Dh = b, *Dl = Dh + eD, *DTh = Dl + eD, *DTl = DTh + eDT, *XTh = DTl + eDT, *XTl = XTh + eXT,
+              *YTh = XTl + eXT, *YTl = YTh + eYT, *WTh = YTl + eYT, *WTl = WTh + eWT;
+        bl::TcOperand D, DT, XT, YT, WT;
+        BL_CHECK(bl::tc_prepare(ctx, pl->deltas, 4 * L, N, 4 * L, /*kmajor=*/false, strict, DTh, DTl, &DT));
+        BL_CHECK(bl::tc_prepare(ctx, X, P, N, ldx, false, strict, XTh, XTl, &XT));
+        BL_CHECK(bl::tc_prepare(ctx, Y, L, N, ldy, false, strict, YTh, YTl, &YT));
+        (void)ldN;
+        // (2) error to the preceding layer: dX[N][P] = deltas[N][4L] * Win^T[P][4L]^T   (the 8 products of :996-1006)
+        if (dX) {
+            BL_CHECK(bl::tc_prepare(ctx, pl->deltas, N, 4 * L, 4 * L, true, strict, Dh, Dl, &D));
+            BL_CHECK(bl::tc_prepare(ctx, W, P, 4 * L, P, false, strict, WTh, WTl, &WT));
+            BL_CHECK(bl::tc_gemm(ctx, N, P, 4 * L, D, 0, 0, WT, 0, 0, dX, lddx, 0));
+        }
+        // (3) input weight gradients: dWin[4L][P] = deltas^T[4L][N] * X^T[P][N]^T   (ComputeWeightUpdateFn case 0x0, :372-389)
+        BL_CHECK(bl::tc_gemm(ctx, 4 * L, P, N, DT, 0, 0, XT, 0, 0, dW, P, 0));
+        // (4) recurrent weight gradients, one [H x H] block per (gate, direction) (case 0x8, :411-437, 493-500):
+        //     fw: dW[j][k] = sum_{n>=S} delta[n,j] * h[n-S,k];   bw: dW[j][k] = sum_{n<N-S} delta[n,j] * h[n+S,k]
+        for (int g = 0; g < 4; ++g)
+            for (int d = 0; d < pl->ndir; ++d) {
+                float *blk = dWint + (size_t)g * L * H + (size_t)d * H * H;
+                if (N - S > 0)
+                    BL_CHECK(bl::tc_gemm(ctx, H, H, N - S, DT, g * L + d * H, d == 0 ? S : 0, YT, d * H, d == 0 ? 0 : S, blk, H, 0));
+                else
+                    BL_CHECK(bl_memset(ctx, blk, 0, (size_t)H * H * sizeof(float)));
+            }
+    } else {
+        // (2) error to the preceding layer: dX[P x N] = Win[P x 4L] * deltas[4L x N]   (the 8 products of :996-1006)
+        // (the optional fast mode only relaxes the forward projections; gradients always use the strict path)
+        if (dX) BL_CHECK(bl_gemm_f32(ctx, 0, 0, P, N, 4 * L, W, P, pl->deltas, 4 * L, dX, lddx, 0, BL_GEMM_STRICT));
+
+        // (3) input weight gradients: dWin[P x 4L] = X[P x N] * deltas^T   (ComputeWeightUpdateFn case 0x0, :372-389)
+        BL_CHECK(bl_gemm_f32(ctx, 0, 1, P, 4 * L, N, X, ldx, pl->deltas, 4 * L, dW, P, 0, BL_GEMM_STRICT));
+
+        // (4) recurrent weight gradients, one [H x H] block per (gate, direction) (case 0x8, :411-437, 493-500):
+        //     fw: dW[k,j] = sum_{n>=S}  h[n-S,k] * delta[n,j];   bw: dW[k,j] = sum_{n<N-S} h[n+S,k] * delta[n,j]
+        for (int g = 0; g < 4; ++g)
+            for (int d = 0; d < pl->ndir; ++d) {
+                float *blk = dWint + (size_t)g * L * H + (size_t)d * H * H;
+                const int col = g * L + d * H;
+                if (N - S > 0) {
+                    const float *A = (d == 0) ? Y : Y + (size_t)S * ldy + H;
+                    const float *B = (d == 0) ? pl->deltas + (size_t)S * 4 * L + col : pl->deltas + col;
+                    BL_CHECK(bl_gemm_f32(ctx, 0, 1, H, H, N - S, A, ldy, B, 4 * L, blk, H, 0, BL_GEMM_STRICT));
+                } else {
+                    BL_CHECK(bl_memset(ctx, blk, 0, (size_t)H * H * sizeof(float)));
+                }
+            }
+    }
 
     // (5) bias + peephole gradients
     {

@@ -52,7 +52,11 @@ def test_gemm_matches_fp64(gpu_ctx, oracle, shape, accumulate):
     B = rng.standard_normal((colsB, ldb)).astype(np.float32)
     C0 = rng.standard_normal((n, ldc)).astype(np.float32)
     dA, dB, dC = gpu_ctx.to_device(A), gpu_ctx.to_device(B), gpu_ctx.to_device(C0)
-    gpu_ctx.gemm(tA, tB, m, n, k, dA, lda, dB, ldb, dC, ldc, accumulate)
+    gpu_ctx.set_gemm_backend(1)                                    # this test pins the SIMT FFMA kernel; the tcgen05 path has its own
+    try:
+        gpu_ctx.gemm(tA, tB, m, n, k, dA, lda, dB, ldb, dC, ldc, accumulate)
+    finally:
+        gpu_ctx.set_gemm_backend(0)
     C = gpu_ctx.to_host(dC, (n, ldc))
     for p in (dA, dB, dC):
         gpu_ctx.free(p)
