@@ -25,6 +25,7 @@ struct bl_lstm_plan {
     int P, L, H, ndir, S, maxT;
     float bias;
     bl::RecGeom gf, gb;
+    bool reg_f, reg_b;       // register-resident persistent kernels (lstm_recurrent_reg.cu) vs shared-memory ones
     float *acts, *deltas, *cst, *cerr, *hx, *dx, *gpart;
     long long *trace;
     float *tcbuf;            // prepared tensor-core operands of the backward pass (hi/lo of deltas, deltas^T, X^T, Y^T, Win^T)
@@ -118,13 +119,17 @@ int bl_lstm_plan_create(bl_ctx *ctx, int P, int L, int bidirectional, int S, int
     pl->tcbuf = nullptr; pl->tcbuf_elems = 0;
 
     const int cap = ctx->smem_optin - 2048;      // room for the kernels' static shared memory (exp table) and the driver's reserve
-    // tuning overrides (tools/sweep_geometry.py): sequence groups and sub-CTAs per CTA of either kernel
+    // tuning overrides (tools/sweep_geometry.py): sequence groups / sub-CTAs / threads of either kernel, and the kernel family
+    // (BLSTM_REC_V=2 forces the shared-memory-resident kernels; default: register-resident weights whenever the slice fits)
     const char *ef = getenv("BLSTM_FWD_G"), *eb = getenv("BLSTM_BWD_G"), *nf = getenv("BLSTM_FWD_NSUB"), *nb = getenv("BLSTM_BWD_NSUB"),
-               *tf = getenv("BLSTM_FWD_NT"), *tb = getenv("BLSTM_BWD_NT");
-    if (!bl::choose_geometry(false, pl->H, S, pl->ndir, ctx->num_sms, cap, ef ? atoi(ef) : 0, nf ? atoi(nf) : 0, tf ? atoi(tf) : 0, &pl->gf) ||
-        !bl::choose_geometry(true, pl->H, S, pl->ndir, ctx->num_sms, cap, eb ? atoi(eb) : 0, nb ? atoi(nb) : 0, tb ? atoi(tb) : 0, &pl->gb)) {
+               *tf = getenv("BLSTM_FWD_NT"), *tb = getenv("BLSTM_BWD_NT"), *ev = getenv("BLSTM_REC_V");
+    const bool want_reg = !(ev && atoi(ev) == 2);
+    pl->reg_f = want_reg && bl::choose_geometry_reg(false, pl->H, S, pl->ndir, ctx->num_sms, cap, ef ? atoi(ef) : 0, &pl->gf);
+    pl->reg_b = want_reg && bl::choose_geometry_reg(true, pl->H, S, pl->ndir, ctx->num_sms, cap, eb ? atoi(eb) : 0, &pl->gb);
+    if ((!pl->reg_f && !bl::choose_geometry(false, pl->H, S, pl->ndir, ctx->num_sms, cap, ef ? atoi(ef) : 0, nf ? atoi(nf) : 0, tf ? atoi(tf) : 0, &pl->gf)) ||
+        (!pl->reg_b && !bl::choose_geometry(true, pl->H, S, pl->ndir, ctx->num_sms, cap, eb ? atoi(eb) : 0, nb ? atoi(nb) : 0, tb ? atoi(tb) : 0, &pl->gb))) {
         delete pl;
-        return bl::fail(ctx, "bl_lstm_plan_create: no persistent-kernel geometry fits (H=%d S=%d): recurrent weights do not fit in shared memory",
+        return bl::fail(ctx, "bl_lstm_plan_create: no persistent-kernel geometry fits (H=%d S=%d): recurrent weights do not fit on chip",
                         L / (bidirectional ? 2 : 1), S);
     }
     const size_t N = (size_t)maxT * S;
@@ -166,8 +171,9 @@ void bl_lstm_plan_destroy(bl_lstm_plan *pl)
 
 int bl_lstm_plan_info(const bl_lstm_plan *pl, int *o)
 {
-    o[0] = pl->gf.G; o[1] = pl->gf.C; o[2] = pl->gf.CL; o[3] = (int)pl->gf.smem + pl->gf.nsub;     // smem is a multiple of 4: low bits carry nsub
-    o[4] = pl->gb.G; o[5] = pl->gb.C; o[6] = pl->gb.CL; o[7] = (int)pl->gb.smem + pl->gb.nsub;
+    // smem is a multiple of 4: the low two bits carry nsub (1, 2, 4 -> 1, 2, 0), or 3 for the register-resident kernels
+    o[0] = pl->gf.G; o[1] = pl->gf.C; o[2] = pl->gf.CL; o[3] = (int)pl->gf.smem + (pl->reg_f ? 3 : pl->gf.nsub);
+    o[4] = pl->gb.G; o[5] = pl->gb.C; o[6] = pl->gb.CL; o[7] = (int)pl->gb.smem + (pl->reg_b ? 3 : pl->gb.nsub);
     return 0;
 }
 
@@ -186,7 +192,7 @@ int bl_lstm_forward(bl_lstm_plan *pl, const float *W, const float *X, int ldx, c
     p.Wb = W + (size_t)4 * L * P; p.Wi = p.Wb + 4 * L; p.Wp = p.Wi + (size_t)4 * L * H;
     p.acts = pl->acts; p.cst = pl->cst; p.Y = Y; p.ldy = ldy; p.hx = pl->hx; p.flags = pl->flags_f; p.pat = patTypes;
     p.T = T; p.Tmin = Tmin; p.S = S; p.H = H; p.L = L; p.ndir = pl->ndir; p.bias = pl->bias; p.g = pl->gf; p.trace = pl->trace;
-    BL_CHECK(bl::launch_lstm_fwd(ctx, p));
+    BL_CHECK(pl->reg_f ? bl::launch_lstm_fwd_reg(ctx, p) : bl::launch_lstm_fwd(ctx, p));
     pl->lastT = T;
     return 0;
 }
@@ -209,7 +215,7 @@ int bl_lstm_backward(bl_lstm_plan *pl, const float *W, const float *X, int ldx, 
     p.acts = pl->acts; p.cst = pl->cst; p.deltas = pl->deltas; p.cerr = pl->cerr; p.dY = dY; p.lddy = lddy;
     p.dx = pl->dx; p.flags = pl->flags_b; p.pat = patTypes;
     p.T = T; p.Tmin = Tmin; p.S = S; p.H = H; p.L = L; p.ndir = pl->ndir; p.g = pl->gb;
-    BL_CHECK(bl::launch_lstm_bwd(ctx, p));
+    BL_CHECK(pl->reg_b ? bl::launch_lstm_bwd_reg(ctx, p) : bl::launch_lstm_bwd(ctx, p));
 
     if (bl::tc_wanted(ctx, P, 4 * L, N)) {
         // ---- tensor-core path: every operand is brought into K-major hi/lo form ONCE per layer and reused:

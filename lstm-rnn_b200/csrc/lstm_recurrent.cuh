@@ -58,6 +58,11 @@ struct RecBwdParams {
     RecGeom g;
 };
 
+// register-resident variant (lstm_recurrent_reg.cu): geometry in the same struct (RQt = row halves, KS = 32-float k chunks)
+bool choose_geometry_reg(bool bwd, int H, int S, int ndir, int num_sms, int smem_cap, int forceG, RecGeom *out);
+int launch_lstm_fwd_reg(bl_ctx *ctx, const RecFwdParams &p);
+int launch_lstm_bwd_reg(bl_ctx *ctx, const RecBwdParams &p);
+
 int launch_lstm_fwd(bl_ctx *ctx, const RecFwdParams &p);
 int launch_lstm_bwd(bl_ctx *ctx, const RecBwdParams &p);
 
