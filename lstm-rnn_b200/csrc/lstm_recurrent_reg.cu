@@ -228,6 +228,9 @@ __global__ void __launch_bounds__(RG_NT, 1) lstm_fwd_reg_kernel(const RecFwdPara
             if (tr && tid == 0) tr[3] = clock64();
         }
 
+        // gate math; only the exchange value h is stored before the publish so that the release fence has as little as
+        // possible to wait for -- the HBM-only results (activations, c, layer output) are stored after it
+        float r_ni[NPAIR], r_ig[NPAIR], r_fg[NPAIR], r_og[NPAIR], r_h[NPAIR];
 #pragma unroll
         for (int u = 0; u < NPAIR; ++u) {
             if (!valid[u]) continue;
@@ -235,6 +238,7 @@ __global__ void __launch_bounds__(RG_NT, 1) lstm_fwd_reg_kernel(const RecFwdPara
             float h, c;
             if (dummy[u]) {                                       // LstmLayer.cu:78-85
                 h = 0.0f; c = 0.0f;
+                r_ni[u] = r_ig[u] = r_fg[u] = r_og[u] = 0.0f;
             } else {
                 float ni = a[u][0], ig = a[u][1], fg = a[u][2], og = a[u][3];
                 if (!first) {                                     // recurrent addProduct, :815-818
@@ -256,16 +260,24 @@ __global__ void __launch_bounds__(RG_NT, 1) lstm_fwd_reg_kernel(const RecFwdPara
                 og = __fadd_rn(og, __fmul_rn(c, wpe[u][2]));      // :129-131
                 og = logistic_fn_tab(og, s_tab);
                 h = __fmul_rn(tanh_fn_tab(c, s_tab), og);         // :134
-                float *ap = acts_t + slot * 4 * L + cl;
-                ap[0] = ni; ap[L] = ig; ap[2 * L] = fg; ap[3 * L] = og;
+                r_ni[u] = ni; r_ig[u] = ig; r_fg[u] = fg; r_og[u] = og;
             }
-            cprev[u] = c;
-            cst_t[slot * L + cl] = c;
-            y_t[slot * p.ldy + cl] = h;
+            cprev[u] = c; r_h[u] = h;
             hx_w[slot * g.RS + rg_koff(j0 + cl)] = h;
         }
         if (tr && tid == 0) tr[4] = clock64();
         if (q + 1 < T) rg_publish(flag);
+#pragma unroll
+        for (int u = 0; u < NPAIR; ++u) {
+            if (!valid[u]) continue;
+            const int slot = s0 + sl_[u], cl = cl_[u];
+            if (!dummy[u]) {
+                float *ap = acts_t + slot * 4 * L + cl;
+                ap[0] = r_ni[u]; ap[L] = r_ig[u]; ap[2 * L] = r_fg[u]; ap[3 * L] = r_og[u];
+            }
+            cst_t[slot * L + cl] = cprev[u];
+            y_t[slot * p.ldy + cl] = r_h[u];
+        }
         if (tr && tid == 0) tr[5] = clock64();
     }
 }
@@ -345,10 +357,10 @@ __global__ void __launch_bounds__(RG_NT, 1) lstm_bwd_reg_kernel(const RecBwdPara
         const char *pat_t = p.pat + (size_t)t * S;
         float *dx_w = p.dx + (size_t)(d * 2 + (q & 1)) * S * g.RS;
 
-        float a[NPAIR][4], c[NPAIR], cp[NPAIR], oe[NPAIR]; bool dummy[NPAIR];
+        float a[NPAIR][4], c[NPAIR], cp[NPAIR], oe[NPAIR], r_dni[NPAIR], r_dog[NPAIR]; bool dummy[NPAIR];
 #pragma unroll
         for (int u = 0; u < NPAIR; ++u) {
-            dummy[u] = false; cp[u] = 0.0f;
+            dummy[u] = false; cp[u] = 0.0f; r_dni[u] = r_dog[u] = 0.0f;
             if (valid[u]) {
                 const int slot = s0 + sl_[u], cl = cl_[u];
                 dummy[u] = check && (pat_t[slot] == BL_PATTYPE_NONE);
@@ -398,14 +410,20 @@ __global__ void __launch_bounds__(RG_NT, 1) lstm_bwd_reg_kernel(const RecBwdPara
                 nfg[u] = fg;
             }
             ncerr[u] = cerr; ndig[u] = dig; ndfg[u] = dfg;
-            float *dp = del_t + slot * 4 * L + cl;
-            dp[0] = dni; dp[L] = dig; dp[2 * L] = dfg; dp[3 * L] = dog;
-            cerr_t[slot * L + cl] = cerr;
-            float *xp = dx_w + slot * g.RS;
+            r_dni[u] = dni; r_dog[u] = dog;
+            float *xp = dx_w + slot * g.RS;                      // exchange values first: the release fence only waits for these
             const int jj = j0 + cl;
             xp[rg_koff(jj)] = dni; xp[rg_koff(Hp + jj)] = dig; xp[rg_koff(2 * Hp + jj)] = dfg; xp[rg_koff(3 * Hp + jj)] = dog;
         }
         if (q + 1 < T) rg_publish(flag);
+#pragma unroll
+        for (int u = 0; u < NPAIR; ++u) {                        // HBM-only results after the publish
+            if (!valid[u]) continue;
+            const int slot = s0 + sl_[u], cl = cl_[u];
+            float *dp = del_t + slot * 4 * L + cl;
+            dp[0] = r_dni[u]; dp[L] = ndig[u]; dp[2 * L] = ndfg[u]; dp[3 * L] = r_dog[u];
+            cerr_t[slot * L + cl] = ncerr[u];
+        }
     }
 }
 

@@ -13,11 +13,12 @@ Configuration &Configuration::instance()
 namespace layers {
 
 // ------------------------------------------------------------------ Layer (layers/Layer.cpp:41-157)
-Layer::Layer(bl_ctx *ctx, const helpers::JsonValue &layerChild, int parallelSequences, int maxSeqLength, bool createOutputs)
+Layer::Layer(bl_ctx *ctx, const helpers::JsonValue &layerChild, int parallelSequences, int maxSeqLength, bool createOutputs, bool padRows)
     : m_ctx(ctx)
     , m_name(layerChild.HasMember("name") ? layerChild["name"].GetString() : "")
     , m_size(layerChild.HasMember("size") ? layerChild["size"].GetInt() : 0)
-    , m_ld(device::paddedLd(layerChild.HasMember("size") ? layerChild["size"].GetInt() : 0))
+    , m_ld(padRows ? device::paddedLd(layerChild.HasMember("size") ? layerChild["size"].GetInt() : 0)
+                   : (layerChild.HasMember("size") ? layerChild["size"].GetInt() : 0))
     , m_parallelSequences(parallelSequences)
     , m_maxSeqLength(maxSeqLength)
     , m_curMaxSeqLength(0)
@@ -84,7 +85,7 @@ std::vector<real_t> Layer::outputErrorsToHost() { return rowsToHost(m_outputErro
 
 // ------------------------------------------------------------------ InputLayer (layers/InputLayer.cpp:31-60)
 InputLayer::InputLayer(bl_ctx *ctx, const helpers::JsonValue &layerChild, int parallelSequences, int maxSeqLength)
-    : Layer(ctx, layerChild, parallelSequences, maxSeqLength)
+    : Layer(ctx, layerChild, parallelSequences, maxSeqLength, true, /*padRows=*/false)
 {
 }
 
@@ -96,9 +97,7 @@ void InputLayer::loadSequences(const data_sets::DataSetFraction &fraction)
         throw std::runtime_error(std::string("Input layer size of ") + std::to_string(this->size())
                                  + " != data input pattern size of " + std::to_string(fraction.inputPatternSize()));
     Layer::loadSequences(fraction);
-    const size_t row = (size_t)size() * sizeof(real_t);
-    check(ctx(), bl_memcpy2d_h2d(ctx(), _outputs().data(), (size_t)ld() * sizeof(real_t), fraction.inputs().data(), row, row,
-                                 (size_t)curPatterns()));
+    _outputs().fromHost(fraction.inputs().data(), (size_t)curPatterns() * size());      // ld() == size(): one contiguous copy
 }
 
 // ------------------------------------------------------------------ TrainableLayer (layers/TrainableLayer.cu:50-248)
@@ -305,7 +304,7 @@ void LstmLayer::planInfo(int *out8) const { bl_lstm_plan_info(m_plan, out8); }
 
 // ------------------------------------------------------------------ PostOutputLayer (layers/PostOutputLayer.cpp:49-79)
 PostOutputLayer::PostOutputLayer(const helpers::JsonValue &layerChild, Layer &precedingLayer, int requiredSize, bool createOutputs)
-    : Layer(precedingLayer.ctx(), layerChild, precedingLayer.parallelSequences(), precedingLayer.maxSeqLength(), createOutputs)
+    : Layer(precedingLayer.ctx(), layerChild, precedingLayer.parallelSequences(), precedingLayer.maxSeqLength(), createOutputs, /*padRows=*/false)
     , m_devScalar(precedingLayer.ctx(), 1)
     , m_precedingLayer(precedingLayer)
 {
@@ -319,11 +318,8 @@ void PostOutputLayer::loadSequences(const data_sets::DataSetFraction &fraction)
         throw std::runtime_error(std::string("Output layer size of ") + std::to_string(this->size())
                                  + " != data target pattern size of " + std::to_string(fraction.outputPatternSize()));
     Layer::loadSequences(fraction);
-    if (!this->_outputs().empty() && !fraction.outputs().empty()) {
-        const size_t row = (size_t)size() * sizeof(real_t);
-        check(ctx(), bl_memcpy2d_h2d(ctx(), _outputs().data(), (size_t)ld() * sizeof(real_t), fraction.outputs().data(), row, row,
-                                     (size_t)curPatterns()));
-    }
+    if (!this->_outputs().empty() && !fraction.outputs().empty())
+        this->_outputs().fromHost(fraction.outputs().data(), (size_t)curPatterns() * size());   // ld() == size()
 }
 
 // ------------------------------------------------------------------ SSE / CE (layers/SsePostOutputLayer.cu, CePostOutputLayer.cu)

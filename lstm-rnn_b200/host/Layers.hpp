@@ -18,7 +18,10 @@ public:
     typedef device::real_vector    real_vector;
     typedef device::pattype_vector pattype_vector;
 
-    Layer(bl_ctx *ctx, const helpers::JsonValue &layerChild, int parallelSequences, int maxSeqLength, bool createOutputs = true);
+    // padRows: pad each pattern row to 16 bytes (layers written by kernels); false for the layers filled by H2D copies
+    // (input layer, dense targets), which then take ONE contiguous copy per fraction instead of a row-strided one
+    Layer(bl_ctx *ctx, const helpers::JsonValue &layerChild, int parallelSequences, int maxSeqLength, bool createOutputs = true,
+          bool padRows = true);
     virtual ~Layer();
 
     const std::string &name() const { return m_name; }
