@@ -205,6 +205,7 @@ def run_ours(args, rank, world, local_rank):
     order = np.random.default_rng(5).permutation(len(fracs))       # shuffle_fractions=true (examples/phoneme_recognition_timit/config.cfg)
     fracs = [fracs[i] for i in order]
     warm, timed = fracs[:W], fracs[W:W + K]
+    warm = [max(timed, key=lambda f: f.N)] + warm          # sizes every scratch buffer before the timed passes
     assert len(timed) == K, "not enough fractions"
 
     def barrier():

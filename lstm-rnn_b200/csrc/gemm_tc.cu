@@ -398,6 +398,7 @@ int tc_gemm(bl_ctx *ctx, int M, int N, int K, const TcOperand &A, int a_row0, in
     const bool strict = A.strict;
     if (A.strict != B.strict) return fail(ctx, "tc_gemm: operands prepared for different precision modes");
     if (a_row0 + M > A.rows || b_row0 + N > B.rows || a_k0 + K > A.K || b_k0 + K > B.K) return fail(ctx, "tc_gemm: sub-view out of range");
+    if ((a_k0 | b_k0) & 3) return fail(ctx, "tc_gemm: K offsets must be multiples of 4 floats (TMA box starts are 16-byte aligned)");
     constexpr int BN_STRICT = 128, BN_FAST = 256;
     const int BN = strict ? BN_STRICT : BN_FAST;
     const int tiles = cdiv(M, TC_BM) * cdiv(N, BN);

@@ -253,9 +253,16 @@ int bl_lstm_backward(bl_lstm_plan *pl, const float *W, const float *X, int ldx, 
         for (int g = 0; g < 4; ++g)
             for (int d = 0; d < pl->ndir; ++d) {
                 float *blk = dWint + (size_t)g * L * H + (size_t)d * H * H;
-                if (N - S > 0)
+                if (N - S > 0 && (S & 3) == 0)
+                    // time shift as a K offset of the sub-view (TMA box starts must stay 16-byte aligned: S % 4 == 0)
                     BL_CHECK(bl::tc_gemm(ctx, H, H, N - S, DT, g * L + d * H, d == 0 ? S : 0, YT, d * H, d == 0 ? 0 : S, blk, H, 0));
-                else
+                else if (N - S > 0) {
+                    // unaligned shift: generic entry (re-prepares the shifted operands from their source pointers)
+                    const int col = g * L + d * H;
+                    const float *A = (d == 0) ? Y : Y + (size_t)S * ldy + H;
+                    const float *B = (d == 0) ? pl->deltas + (size_t)S * 4 * L + col : pl->deltas + col;
+                    BL_CHECK(bl_gemm_f32(ctx, 0, 1, H, H, N - S, A, ldy, B, 4 * L, blk, H, 0, BL_GEMM_STRICT));
+                } else
                     BL_CHECK(bl_memset(ctx, blk, 0, (size_t)H * H * sizeof(float)));
             }
     } else {

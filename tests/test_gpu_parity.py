@@ -300,3 +300,111 @@ def test_network_parity_with_tensor_core_gemms(oracle, gpu_ctx):
     finally:
         gpu_ctx.set_gemm_mode(0)
         gpu_ctx.set_gemm_backend(0)
+
+
+# ----------------------------------------------------------------------------- BASELINE.json configs at (or near) full size
+def _full_net(gpu_ctx, name, S, maxT):
+    import currennt_b200 as cb
+    cfg = synth.config(name)
+    net = cb.Net(gpu_ctx, cfg["net"], S, maxT)
+    weights = synth.init_weights(cfg["net"], 77)
+    for i, w in enumerate(weights):
+        if len(w):
+            net.set_weights(i, w)
+    return cfg, net, weights
+
+
+def test_c2_network_against_oracle_short_sequences(oracle, gpu_ctx):
+    """The full TIMIT-shape network (123 -> 3 x blstm 500 -> softmax 183, S=100) against the oracle on a fraction short enough
+    for the CPU oracle (T=10): every tensor within the strict bar.  Exercises the production geometry (G=9 x C=8 slices,
+    register-resident weights) and the tcgen05 GEMMs at their real M/N."""
+    cfg = synth.config("C2")
+    rng = np.random.default_rng(3)
+    lengths = sorted(rng.integers(6, 11, 100).tolist())
+    worst = check_net(oracle, gpu_ctx, cfg["net"], 100, lengths, 183, 0, seed=21)
+    print("C2 full-width worst rel err %.2e" % worst)
+
+
+def test_c2_full_size_properties(gpu_ctx):
+    """Size-independent properties on a full-size C2 fraction (S=100, T up to ~300, N ~ 30 000 slots):
+    additivity of the gradient over a split of the sequences (the data-parallel property, LstmLayer.cu:502-510),
+    softmax rows summing to one, exact zeros on padded slots, objective == -sum log p[target] recomputed on the host,
+    argmax count recomputed on the host, and run-to-run determinism."""
+    import currennt_b200 as cb
+    S = 100
+    cfg = synth.config("C2")
+    lengths = np.sort(synth.sequence_lengths(cfg, S, 9))
+    lengths = np.minimum(lengths, 320)
+    xs, cs, _ = synth.make_sequences(lengths, 123, 5, classes=183)
+    T = int(lengths.max())
+    _, net, weights = _full_net(gpu_ctx, "C2", S, T)
+    ds = cb.DataSet(gpu_ctx, xs, S, seq_classes=cs, O=183, training=True)
+    frac = ds.next_fraction()
+    net.load_fraction(frac); net.forward()
+    err = net.calculate_error(); correct = net.count_correct(); net.backward()
+    y = net.get_outputs(4)
+    inputs, pat, tc, _, _ = frac.arrays(True)
+    valid = pat != 0
+    assert np.allclose(y[valid].sum(1), 1.0, atol=2e-6)                       # softmax rows
+    p_t = y[np.arange(len(tc))[valid], tc[valid]].astype(np.float64)
+    assert abs(err - float(-np.log(np.maximum(p_t, 1.1754944e-38)).sum())) <= 2e-5 * abs(err)
+    assert correct == int((y[valid].argmax(1) == tc[valid]).sum())
+    for i in (1, 2, 3):
+        pad = (~valid) & (np.arange(frac.N) // S >= frac.Tmin)
+        assert not net.get_outputs(i)[pad].any()                               # padded slots of every BLSTM layer are exact zeros
+    g_full = [net.get_weight_updates(i) for i in range(1, 5)]
+    assert all(np.isfinite(g).all() for g in g_full)
+    # determinism
+    net.load_fraction(frac); net.forward(); net.calculate_error(); net.backward()
+    for a, i in zip(g_full, range(1, 5)):
+        assert np.array_equal(a, net.get_weight_updates(i))
+    # additivity over a split of the sequences into two networks of S/2 (what two data-parallel ranks would compute)
+    half = S // 2
+    g_sum = [np.zeros_like(g, dtype=np.float64) for g in g_full]
+    e_sum, c_sum = 0.0, 0
+    for r in range(2):
+        _, hnet, _ = _full_net(gpu_ctx, "C2", half, T)
+        hds = cb.DataSet(gpu_ctx, xs, half, seq_classes=cs, O=183, training=True, rank=r, world=2)
+        hf = hds.next_fraction()
+        hnet.load_fraction(hf); hnet.forward(); e_sum += hnet.calculate_error(); c_sum += hnet.count_correct(); hnet.backward()
+        for k, i in enumerate(range(1, 5)):
+            g_sum[k] += hnet.get_weight_updates(i)
+        del hnet
+    assert c_sum == correct and abs(e_sum - err) <= 1e-5 * abs(err)
+    for a, b in zip(g_sum, g_full):
+        assert rel_err(a, b) <= 2e-5
+
+
+def test_c1_shape_epoch_tracks_oracle(oracle, gpu_ctx):
+    """tests/test1 recipe (39 -> blstm10 -> tanh5 -> blstm10 -> tanh5 -> blstm10 -> softmax51, S=10, hybrid online/batch,
+    momentum 0.9) on a synthetic twin of val_1_speaker.nc cut to 40 short sequences: after one epoch of 4 fractions the
+    weights still track the oracle's."""
+    import currennt_b200 as cb
+    cfg = synth.config("C1")
+    S, lr, mom = 10, 1e-3, 0.9
+    rng = np.random.default_rng(1)
+    lengths = np.sort(rng.integers(12, 31, 40))
+    xs, cs, _ = synth.make_sequences(lengths, 39, 1, classes=51)
+    weights = synth.init_weights(cfg["net"], 2)
+    maxT = int(lengths.max())
+    orc, gpu = oracle.OracleNet(cfg["net"], S, maxT), cb.Net(gpu_ctx, cfg["net"], S, maxT)
+    for i, w in enumerate(weights):
+        if len(w):
+            orc.set_weights(i, w); gpu.set_weights(i, w)
+    opt = cb.Optimizer(gpu, lr, mom, hybrid=True)
+    ds = cb.DataSet(gpu_ctx, xs, S, seq_classes=cs, O=51, training=True)
+    e_gpu, ce_gpu = opt.process_dataset(ds, train=True)
+    deltas = [np.zeros_like(w) for w in weights]
+    e_orc, correct = 0.0, 0
+    for fi in range(4):
+        f = oracle.make_fraction(xs, S, fi * S, seq_classes=cs, O=51)
+        orc.load_fraction(f); orc.forward(); e_orc += orc.calculate_error(); correct += orc.count_correct(); orc.backward()
+        orc.sgd_update(deltas, lr, mom)
+    assert abs(e_gpu - e_orc / 40) <= 1e-5 * abs(e_orc / 40)                   # error / totalSequences (Optimizer.cu:99)
+    assert abs(ce_gpu - (1.0 - correct / lengths.sum())) <= 1e-6                # 1 - correct / totalTimesteps (Optimizer.cu:100)
+    # the 5-unit tanh layers of this recipe sit on the 2^-23 activation grid (helpers.ACT_GRID): a one-step flip moves the
+    # gradients behind them by ~2e-5 relative, so the accumulated UPDATE (not the weight) is the quantity held to 1e-4
+    for i, w in enumerate(weights):
+        if len(w):
+            assert rel_err(gpu.get_weights(i), orc.get_weights(i)) <= 1e-4
+            assert rel_err(gpu.get_weights(i) - w, orc.get_weights(i) - w) <= 2e-3
