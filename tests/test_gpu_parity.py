@@ -396,15 +396,19 @@ def test_c1_shape_epoch_tracks_oracle(oracle, gpu_ctx):
     e_gpu, ce_gpu = opt.process_dataset(ds, train=True)
     deltas = [np.zeros_like(w) for w in weights]
     e_orc, correct = 0.0, 0
+    ds2 = cb.DataSet(gpu_ctx, xs, S, seq_classes=cs, O=51, training=True)     # same (unstable) sort by length as the run above
     for fi in range(4):
-        f = oracle.make_fraction(xs, S, fi * S, seq_classes=cs, O=51)
+        pf = ds2.next_fraction()
+        inputs, pat, tc, _, lens = pf.arrays(True)
+        f = oracle.Fraction(S, pf.T, pf.Tmin, lens, 39, 51, inputs, pat, tc)
         orc.load_fraction(f); orc.forward(); e_orc += orc.calculate_error(); correct += orc.count_correct(); orc.backward()
         orc.sgd_update(deltas, lr, mom)
     assert abs(e_gpu - e_orc / 40) <= 1e-5 * abs(e_orc / 40)                   # error / totalSequences (Optimizer.cu:99)
     assert abs(ce_gpu - (1.0 - correct / lengths.sum())) <= 1e-6                # 1 - correct / totalTimesteps (Optimizer.cu:100)
-    # the 5-unit tanh layers of this recipe sit on the 2^-23 activation grid (helpers.ACT_GRID): a one-step flip moves the
-    # gradients behind them by ~2e-5 relative, so the accumulated UPDATE (not the weight) is the quantity held to 1e-4
     for i, w in enumerate(weights):
         if len(w):
-            assert rel_err(gpu.get_weights(i), orc.get_weights(i)) <= 1e-4
-            assert rel_err(gpu.get_weights(i) - w, orc.get_weights(i) - w) <= 2e-3
+            # (w - w0 would be dominated by fp32 weight quantisation for the vanishing-gradient layers: compare the momentum state)
+            rw = rel_err(gpu.get_weights(i), orc.get_weights(i))
+            rd = rel_err(opt.weight_deltas(i), deltas[i])
+            print("layer", i, "weights rel err %.2e, momentum-state rel err %.2e" % (rw, rd))
+            assert rw <= 1e-6 and rd <= 1e-5
