@@ -18,6 +18,7 @@
 #include "gemm_tc.cuh"
 #include <cuda.h>
 #include <cstdint>
+#include <cstdlib>
 
 namespace bl {
 
@@ -28,6 +29,8 @@ struct GemmTcParams {
     float *C; int ldc;
     int M, N, K;
     int a_k0, b_k0;                          // element offsets added to the K coordinate of the A / B boxes (time-shifted operands)
+    int batches, mt_per_batch;               // grid.y = batches * mt_per_batch: batch b multiplies A rows [b*a_batch_rows, +M) by the same B
+    int a_batch_rows; long long c_batch_stride;   // and writes its [M x N] block at C + b*c_batch_stride
     int kblocks_per_split;
     int accumulate;
     float *partial; int ldp;                 // split-K: slice z at partial + z*M*ldp
@@ -129,7 +132,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tf32_tcgen05_kernel(const 
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tmem_full + 1);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int n0 = blockIdx.x * BN, m0 = blockIdx.y * TC_BM;
+    const int batch = blockIdx.y / p.mt_per_batch;
+    const int n0 = blockIdx.x * BN, m0 = (blockIdx.y - batch * p.mt_per_batch) * TC_BM;      // m0: row inside the batch's block
+    const int a_row0 = batch * p.a_batch_rows + m0;                                            // row in the A tensor map
     const int kb_total = (p.K + TC_BK - 1) / TC_BK;
     const int kb_begin = blockIdx.z * p.kblocks_per_split;
     const int kb_end = min(kb_total, kb_begin + p.kblocks_per_split);
@@ -166,10 +171,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tf32_tcgen05_kernel(const 
                 uint8_t *st = smem + s * STAGE_BYTES;
                 mbar_expect_tx(&full[s], STAGE_BYTES);
                 const int kc = (kb_begin + i) * TC_BK;
-                tma_load_2d(st, &p.tmA, &full[s], kc + p.a_k0, m0);
+                tma_load_2d(st, &p.tmA, &full[s], kc + p.a_k0, a_row0);
                 tma_load_2d(st + A_BYTES, &p.tmB, &full[s], kc + p.b_k0, n0);
                 if (STRICT) {
-                    tma_load_2d(st + A_BYTES + B_BYTES, &p.tmAlo, &full[s], kc + p.a_k0, m0);
+                    tma_load_2d(st + A_BYTES + B_BYTES, &p.tmAlo, &full[s], kc + p.a_k0, a_row0);
                     tma_load_2d(st + 2 * A_BYTES + B_BYTES, &p.tmBlo, &full[s], kc + p.b_k0, n0);
                 }
             }
@@ -211,7 +216,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tf32_tcgen05_kernel(const 
             mbar_wait(tmem_full, 0);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         }
-        float *out = p.partial ? p.partial + (size_t)blockIdx.z * p.M * p.ldp : p.C;
+        float *out = p.partial ? p.partial + ((size_t)blockIdx.z * p.batches + batch) * p.M * p.ldp : p.C + (size_t)batch * p.c_batch_stride;
         const int ldo = p.partial ? p.ldp : p.ldc;
         const bool acc = (!p.partial) && p.accumulate;
         const bool vec_ok = ((ldo & 3) == 0) && ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
@@ -303,15 +308,16 @@ __global__ void prep_transpose_kernel(int K, int rows, const float *__restrict__
     }
 }
 
-__global__ void sum_slices_kernel(int M, int N, int nsplit, const float *__restrict__ partial, int ldp,
-                                  float *__restrict__ C, int ldc, int accumulate)
+__global__ void sum_slices_kernel(int M, int N, int nsplit, int batches, const float *__restrict__ partial, int ldp,
+                                  float *__restrict__ C, int ldc, long long c_batch_stride, int accumulate)
 {
     const size_t total = (size_t)M * N;
+    const int b = blockIdx.y;
     for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
         const size_t r = e / N, c = e % N;
         float s = 0.0f;
-        for (int z = 0; z < nsplit; ++z) s += partial[((size_t)z * M + r) * ldp + c];      // fixed order: deterministic
-        float *o = C + r * ldc + c;
+        for (int z = 0; z < nsplit; ++z) s += partial[(((size_t)z * batches + b) * M + r) * ldp + c];      // fixed order: deterministic
+        float *o = C + (size_t)b * c_batch_stride + r * ldc + c;
         *o = accumulate ? *o + s : s;
     }
 }
@@ -394,14 +400,24 @@ int tc_prepare(bl_ctx *ctx, const float *src, int rows, int K, size_t ld_src, bo
 int tc_gemm(bl_ctx *ctx, int M, int N, int K, const TcOperand &A, int a_row0, int a_k0, const TcOperand &B, int b_row0, int b_k0,
             float *C, int ldc, int accumulate)
 {
+    return tc_gemm_batched(ctx, M, N, K, A, a_row0, a_k0, B, b_row0, b_k0, C, ldc, accumulate, 1, 0, 0);
+}
+
+// `batches` products sharing B: batch b uses A rows [a_row0 + b*a_batch_rows, +M) and writes C + b*c_batch_stride
+int tc_gemm_batched(bl_ctx *ctx, int M, int N, int K, const TcOperand &A, int a_row0, int a_k0, const TcOperand &B, int b_row0, int b_k0,
+                    float *C, int ldc, int accumulate, int batches, int a_batch_rows, long long c_batch_stride)
+{
     TimedRegion timed(ctx, 0);
     const bool strict = A.strict;
     if (A.strict != B.strict) return fail(ctx, "tc_gemm: operands prepared for different precision modes");
-    if (a_row0 + M > A.rows || b_row0 + N > B.rows || a_k0 + K > A.K || b_k0 + K > B.K) return fail(ctx, "tc_gemm: sub-view out of range");
+    const int a_rows_total = (batches - 1) * a_batch_rows + M;
+    if (a_row0 + a_rows_total > A.rows || b_row0 + N > B.rows || a_k0 + K > A.K || b_k0 + K > B.K) return fail(ctx, "tc_gemm: sub-view out of range");
     if ((a_k0 | b_k0) & 3) return fail(ctx, "tc_gemm: K offsets must be multiples of 4 floats (TMA box starts are 16-byte aligned)");
-    constexpr int BN_STRICT = 128, BN_FAST = 256;
+    // strict tiles: BLSTM_TC_BN=256 selects 128x256 tiles with a 2-stage ring (less L2 traffic per MMA, half the per-tile overhead)
+    static const int bn_strict_env = getenv("BLSTM_TC_BN") ? atoi(getenv("BLSTM_TC_BN")) : 128;
+    const int BN_STRICT = (bn_strict_env == 256) ? 256 : 128; constexpr int BN_FAST = 256;
     const int BN = strict ? BN_STRICT : BN_FAST;
-    const int tiles = cdiv(M, TC_BM) * cdiv(N, BN);
+    const int tiles = batches * cdiv(M, TC_BM) * cdiv(N, BN);
     const int kb_total = cdiv(K, TC_BK);
     int nsplit = 1;
     if (tiles < ctx->num_sms && kb_total >= 16) {
@@ -416,25 +432,27 @@ int tc_gemm(bl_ctx *ctx, int M, int N, int K, const TcOperand &A, int a_row0, in
     GemmTcParams p;
     p.partial = nullptr;
     if (nsplit > 1) {
-        BL_CHECK(ensure_scratch2(ctx, (size_t)nsplit * M * ldp * sizeof(float) + 64));
+        BL_CHECK(ensure_scratch2(ctx, (size_t)nsplit * batches * M * ldp * sizeof(float) + 64));
         p.partial = reinterpret_cast<float *>((reinterpret_cast<uintptr_t>(ctx->scratch2) + 15) & ~(uintptr_t)15);
     }
     // the maps cover rows [row0, row0+M) and K extent [0, k0+K): boxes running past either edge are zero-filled
-    BL_CHECK(make_map(ctx, &p.tmA, A.hi + (size_t)a_row0 * A.ld, M, a_k0 + K, A.ld, TC_BM));
+    BL_CHECK(make_map(ctx, &p.tmA, A.hi + (size_t)a_row0 * A.ld, a_rows_total, a_k0 + K, A.ld, TC_BM));
     BL_CHECK(make_map(ctx, &p.tmB, B.hi + (size_t)b_row0 * B.ld, N, b_k0 + K, B.ld, BN));
     if (strict) {
-        BL_CHECK(make_map(ctx, &p.tmAlo, A.lo + (size_t)a_row0 * A.ld, M, a_k0 + K, A.ld, TC_BM));
+        BL_CHECK(make_map(ctx, &p.tmAlo, A.lo + (size_t)a_row0 * A.ld, a_rows_total, a_k0 + K, A.ld, TC_BM));
         BL_CHECK(make_map(ctx, &p.tmBlo, B.lo + (size_t)b_row0 * B.ld, N, b_k0 + K, B.ld, BN));
     } else { p.tmAlo = p.tmA; p.tmBlo = p.tmB; }
     p.C = C; p.ldc = ldc; p.M = M; p.N = N; p.K = K; p.a_k0 = a_k0; p.b_k0 = b_k0;
     p.kblocks_per_split = kbs; p.accumulate = accumulate; p.ldp = (int)ldp;
-    dim3 grid(cdiv(N, BN), cdiv(M, TC_BM), nsplit);
+    p.batches = batches; p.mt_per_batch = cdiv(M, TC_BM); p.a_batch_rows = a_batch_rows; p.c_batch_stride = c_batch_stride;
+    dim3 grid(cdiv(N, BN), batches * cdiv(M, TC_BM), nsplit);
     if (grid.y > 65535) return fail(ctx, "tc_gemm: M too large");
-    if (strict) BL_CHECK((launch_tc<BN_STRICT, true, 3>(ctx, p, grid)));
+    if (strict && BN_STRICT == 256) BL_CHECK((launch_tc<256, true, 2>(ctx, p, grid)));
+    else if (strict) BL_CHECK((launch_tc<128, true, 3>(ctx, p, grid)));
     else        BL_CHECK((launch_tc<BN_FAST, false, 4>(ctx, p, grid)));
     if (nsplit > 1) {
         int blocks = (int)cdivz((size_t)M * N, 256); if (blocks > 2048) blocks = 2048;
-        sum_slices_kernel<<<blocks, 256, 0, ctx->stream>>>(M, N, nsplit, p.partial, (int)ldp, C, ldc, accumulate);
+        sum_slices_kernel<<<dim3(blocks, batches), 256, 0, ctx->stream>>>(M, N, nsplit, batches, p.partial, (int)ldp, C, ldc, c_batch_stride, accumulate);
         BL_LAUNCHED(ctx);
     }
     return 0;

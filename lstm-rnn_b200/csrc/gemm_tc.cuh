@@ -18,6 +18,8 @@ size_t tc_operand_ld(int K);
 int tc_prepare(bl_ctx *ctx, const float *src, int rows, int K, size_t ld_src, bool kmajor, bool strict, float *hi, float *lo, TcOperand *out);
 int tc_gemm(bl_ctx *ctx, int M, int N, int K, const TcOperand &A, int a_row0, int a_k0, const TcOperand &B, int b_row0, int b_k0,
             float *C, int ldc, int accumulate);
+int tc_gemm_batched(bl_ctx *ctx, int M, int N, int K, const TcOperand &A, int a_row0, int a_k0, const TcOperand &B, int b_row0, int b_k0,
+                    float *C, int ldc, int accumulate, int batches, int a_batch_rows, long long c_batch_stride);
 int gemm_tf32_tc(bl_ctx *ctx, int M, int N, int K, const float *A, size_t lda, bool a_kmajor, const float *B, size_t ldb, bool b_kmajor,
                  float *C, int ldc, int accumulate, int mode);
 // true when bl_gemm_f32 would route an m x n x k contraction to the tensor-core path

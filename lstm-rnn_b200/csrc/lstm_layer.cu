@@ -250,21 +250,26 @@ int bl_lstm_backward(bl_lstm_plan *pl, const float *W, const float *X, int ldx, 
         BL_CHECK(bl::tc_gemm(ctx, 4 * L, P, N, DT, 0, 0, XT, 0, 0, dW, P, 0));
         // (4) recurrent weight gradients, one [H x H] block per (gate, direction) (case 0x8, :411-437, 493-500):
         //     fw: dW[j][k] = sum_{n>=S} delta[n,j] * h[n-S,k];   bw: dW[j][k] = sum_{n<N-S} delta[n,j] * h[n+S,k]
-        for (int g = 0; g < 4; ++g)
-            for (int d = 0; d < pl->ndir; ++d) {
-                float *blk = dWint + (size_t)g * L * H + (size_t)d * H * H;
-                if (N - S > 0 && (S & 3) == 0)
-                    // time shift as a K offset of the sub-view (TMA box starts must stay 16-byte aligned: S % 4 == 0)
-                    BL_CHECK(bl::tc_gemm(ctx, H, H, N - S, DT, g * L + d * H, d == 0 ? S : 0, YT, d * H, d == 0 ? 0 : S, blk, H, 0));
-                else if (N - S > 0) {
-                    // unaligned shift: generic entry (re-prepares the shifted operands from their source pointers)
-                    const int col = g * L + d * H;
-                    const float *A = (d == 0) ? Y : Y + (size_t)S * ldy + H;
-                    const float *B = (d == 0) ? pl->deltas + (size_t)S * 4 * L + col : pl->deltas + col;
-                    BL_CHECK(bl_gemm_f32(ctx, 0, 1, H, H, N - S, A, ldy, B, 4 * L, blk, H, 0, BL_GEMM_STRICT));
-                } else
-                    BL_CHECK(bl_memset(ctx, blk, 0, (size_t)H * H * sizeof(float)));
-            }
+        if (N - S > 0 && (S & 3) == 0) {
+            // one launch per direction: the 4 gate blocks are row sub-views of deltas^T (L rows apart) sharing the same shifted Y^T;
+            // the time shift is a K offset of the sub-view (TMA box starts must stay 16-byte aligned: S % 4 == 0)
+            for (int d = 0; d < pl->ndir; ++d)
+                BL_CHECK(bl::tc_gemm_batched(ctx, H, H, N - S, DT, d * H, d == 0 ? S : 0, YT, d * H, d == 0 ? 0 : S,
+                                             dWint + (size_t)d * H * H, H, 0, /*batches=*/4, /*a_batch_rows=*/L, /*c_batch_stride=*/(long long)L * H));
+        } else {
+            for (int g = 0; g < 4; ++g)
+                for (int d = 0; d < pl->ndir; ++d) {
+                    float *blk = dWint + (size_t)g * L * H + (size_t)d * H * H;
+                    if (N - S > 0) {
+                        // unaligned shift: generic entry (re-prepares the shifted operands from their source pointers)
+                        const int col = g * L + d * H;
+                        const float *A = (d == 0) ? Y : Y + (size_t)S * ldy + H;
+                        const float *B = (d == 0) ? pl->deltas + (size_t)S * 4 * L + col : pl->deltas + col;
+                        BL_CHECK(bl_gemm_f32(ctx, 0, 1, H, H, N - S, A, ldy, B, 4 * L, blk, H, 0, BL_GEMM_STRICT));
+                    } else
+                        BL_CHECK(bl_memset(ctx, blk, 0, (size_t)H * H * sizeof(float)));
+                }
+        }
     } else {
         // (2) error to the preceding layer: dX[P x N] = Win[P x 4L] * deltas[4L x N]   (the 8 products of :996-1006)
         // (the optional fast mode only relaxes the forward projections; gradients always use the strict path)
