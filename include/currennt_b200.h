@@ -63,6 +63,9 @@ int  cn_fraction_get(const cn_fraction *frac, float *inputs, char *pat_types, in
 cn_dataset *cn_dataset_create(bl_ctx *ctx, int num_seqs, const int *seq_lengths, int P, int O, const float *inputs,
                               const int *target_classes, const float *targets, int parallel_sequences, int truncate_seq,
                               int training_mode, int rank, int world);
+/* NetCDF-3 classic data files in the reference's schema (data_sets/DataSet.cpp:443-606); `path` may be a comma separated list */
+cn_dataset *cn_dataset_load_netcdf(bl_ctx *ctx, const char *path, int parallel_sequences, float fraction, int truncate_seq,
+                                   int training_mode, int rank, int world);
 void cn_dataset_destroy(cn_dataset *ds);
 /* out6 = {totalSequences, totalTimesteps, minSeqLength, maxSeqLength, numFractions, isClassification} */
 int  cn_dataset_info(const cn_dataset *ds, long *out6);

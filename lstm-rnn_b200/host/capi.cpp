@@ -4,6 +4,7 @@
 #include <memory>
 #include <string>
 #include "DataSet.hpp"
+#include "NetCdf.hpp"
 #include "NeuralNetwork.hpp"
 #include "Optimizer.hpp"
 
@@ -187,6 +188,18 @@ cn_dataset *cn_dataset_create(bl_ctx *ctx, int numSeqs, const int *seqLengths, i
     CN_TRY
     std::unique_ptr<cn_dataset> d(new cn_dataset);
     d->ds.reset(new data_sets::DataSet(ctx, numSeqs, seqLengths, P, O, inputs, tc, targets, parSeq, trunc, training != 0, rank, world));
+    return d.release();
+    CN_CATCH(nullptr)
+}
+cn_dataset *cn_dataset_load_netcdf(bl_ctx *ctx, const char *path, int parSeq, float fraction, int trunc, int training, int rank, int world)
+{
+    CN_TRY
+    std::unique_ptr<cn_dataset> d(new cn_dataset);
+    std::vector<std::string> files;
+    std::string all(path);                                   // comma separated list, like the reference's --train_file
+    size_t pos = 0;
+    while (pos <= all.size()) { size_t c = all.find(',', pos); if (c == std::string::npos) c = all.size(); if (c > pos) files.push_back(all.substr(pos, c - pos)); pos = c + 1; }
+    d->ds = data_sets::loadNetCdfDataSet(ctx, files, parSeq, fraction, trunc, training != 0, rank, world);
     return d.release();
     CN_CATCH(nullptr)
 }

@@ -106,6 +106,8 @@ def libs():
         h.cn_fraction_get.argtypes = [vp, fp, cp, ip, fp, ip]
         h.cn_dataset_create.restype = vp
         h.cn_dataset_create.argtypes = [vp, ci, ip, ci, ci, fp, ip, fp, ci, ci, ci, ci, ci]
+        h.cn_dataset_load_netcdf.restype = vp
+        h.cn_dataset_load_netcdf.argtypes = [vp, cp, ci, cf, ci, ci, ci, ci]
         h.cn_dataset_destroy.argtypes = [vp]
         h.cn_dataset_info.argtypes = [vp, lp]
         h.cn_dataset_sequence_lengths.argtypes = [vp, ip, ci]
@@ -253,6 +255,20 @@ class DataSet:
         info = (ctypes.c_long * 6)()
         self.h.cn_dataset_info(self.p, info)
         self.total_sequences, self.total_timesteps, self.min_len, self.max_len, self.num_fractions, _ = [int(x) for x in info]
+
+    @classmethod
+    def from_netcdf(cls, ctx, path, S, fraction=1.0, truncate=0, training=True, rank=0, world=1):
+        self = cls.__new__(cls)
+        self.k, self.h = libs()
+        self.ctx = ctx
+        self.p = self.h.cn_dataset_load_netcdf(ctx.p if ctx else None, path.encode(), S, fraction, truncate, int(training), rank, world)
+        if not self.p:
+            raise _herr(self.h)
+        info = (ctypes.c_long * 6)()
+        self.h.cn_dataset_info(self.p, info)
+        self.total_sequences, self.total_timesteps, self.min_len, self.max_len, self.num_fractions, c = [int(x) for x in info]
+        self.classification = bool(c)
+        return self
 
     def sequence_lengths(self):
         out = np.zeros(self.total_sequences, np.int32)
