@@ -67,6 +67,8 @@ int  bl_ctx_set_gemm_mode(bl_ctx *ctx, int mode);
  * 1 = SIMT only, 2 = tcgen05 always (tests).  The precision mode applies to either backend. */
 int  bl_ctx_set_gemm_backend(bl_ctx *ctx, int backend);
 int  bl_ctx_num_sms(const bl_ctx *ctx);
+/* number of CUDA devices visible to the process (--list_devices, main.cpp:509-524); 0 when there is no usable driver */
+int  bl_device_count(void);
 /* number of kernels this library has launched on the context since creation (bench.py gpu_launches) */
 long bl_ctx_launch_count(const bl_ctx *ctx);
 
@@ -179,6 +181,8 @@ int bl_vector_add(bl_ctx *ctx, size_t n, const float *x, float *y);
 int  bl_comm_unique_id(void *id128);
 int  bl_comm_create(bl_ctx *ctx, int rank, int world, const void *id128, bl_comm **out);
 void bl_comm_destroy(bl_comm *comm);
+/* rank / world size of the communicator (either pointer may be NULL) */
+void bl_comm_info(const bl_comm *comm, int *rank, int *world);
 /* In-place sum over ranks of `count` floats on the communicator's side stream, ordered after the work
  * already enqueued on the context's stream; returns immediately. */
 int  bl_allreduce_sum_f32(bl_comm *comm, float *buf, size_t count);

@@ -87,6 +87,12 @@ int bl_comm_create(bl_ctx *ctx, int rank, int world, const void *id128, bl_comm 
     return 0;
 }
 
+void bl_comm_info(const bl_comm *comm, int *rank, int *world)
+{
+    if (rank) *rank = comm ? comm->rank : 0;
+    if (world) *world = comm ? comm->world : 1;
+}
+
 void bl_comm_destroy(bl_comm *c)
 {
     if (!c) return;

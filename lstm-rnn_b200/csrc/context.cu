@@ -139,6 +139,7 @@ int bl_ctx_set_gemm_backend(bl_ctx *ctx, int backend)
 }
 
 int bl_ctx_num_sms(const bl_ctx *ctx) { return ctx->num_sms; }
+int bl_device_count(void) { int n = 0; return cudaGetDeviceCount(&n) == cudaSuccess ? n : 0; }
 long bl_ctx_launch_count(const bl_ctx *ctx) { return ctx->launches; }
 
 int bl_malloc(bl_ctx *ctx, void **ptr, size_t bytes)
@@ -162,7 +163,12 @@ int bl_memcpy2d_d2h(bl_ctx *ctx, void *dst, size_t dp, const void *src, size_t s
     if (rb && rows) BL_CUDA(ctx, cudaMemcpy2DAsync(dst, dp, src, sp, rb, rows, cudaMemcpyDeviceToHost, ctx->stream));
     return 0;
 }
-int bl_malloc_host(bl_ctx *ctx, void **ptr, size_t bytes) { BL_CUDA(ctx, cudaMallocHost(ptr, bytes ? bytes : 1)); return 0; }
+int bl_malloc_host(bl_ctx *ctx, void **ptr, size_t bytes)
+{
+    if (ctx) BL_CUDA(ctx, cudaSetDevice(ctx->device));      // may be called from a prefetch thread that has no current device yet
+    BL_CUDA(ctx, cudaMallocHost(ptr, bytes ? bytes : 1));
+    return 0;
+}
 int bl_free_host(bl_ctx *ctx, void *ptr) { if (ptr) BL_CUDA(ctx, cudaFreeHost(ptr)); return 0; }
 
 } // extern "C"

@@ -2,6 +2,8 @@
 #include <algorithm>
 #include <cstring>
 #include <limits>
+#include <map>
+#include <mutex>
 #include <stdexcept>
 
 namespace data_sets {
@@ -25,6 +27,31 @@ DataSetFraction *DataSetFraction::fromPacked(bl_ctx *ctx, int S, int T, int Tmin
     return f;
 }
 
+namespace {
+std::mutex g_poolMutex;
+std::multimap<size_t, void *> &pool() { static std::multimap<size_t, void *> *p = new std::multimap<size_t, void *>; return *p; }   // never destroyed: outlives the CUDA context
+}
+
+void *DataSetFraction::PinnedPool::get(bl_ctx *ctx, size_t bytes, size_t *capacity)
+{
+    if (bytes == 0) bytes = 1;
+    {
+        std::lock_guard<std::mutex> lock(g_poolMutex);
+        auto it = pool().lower_bound(bytes);
+        if (it != pool().end() && it->first <= 2 * bytes + 4096) { void *p = it->second; *capacity = it->first; pool().erase(it); return p; }
+    }
+    void *p = nullptr;
+    device::check(ctx, bl_malloc_host(ctx, &p, bytes));
+    *capacity = bytes;
+    return p;
+}
+
+void DataSetFraction::PinnedPool::put(void *ptr, size_t capacity)
+{
+    std::lock_guard<std::mutex> lock(g_poolMutex);
+    pool().emplace(capacity, ptr);
+}
+
 static bool comp_seqs(const DataSet::sequence_t &a, const DataSet::sequence_t &b) { return a.length < b.length; }   // DataSet.cpp:165-168
 
 DataSet::DataSet(bl_ctx *ctx, int numSeqs, const int *seqLengths, int P, int O, const real_t *inputs, const int *targetClasses,
@@ -33,6 +60,7 @@ DataSet::DataSet(bl_ctx *ctx, int numSeqs, const int *seqLengths, int P, int O, 
     , m_totalSequences(0), m_totalTimesteps(0)
     , m_minSeqLength(std::numeric_limits<int>::max()), m_maxSeqLength(std::numeric_limits<int>::min())
     , m_inputPatternSize(P), m_outputPatternSize(O), m_curFirstSeqIdx(-1)
+    , m_fractionShuffling(false), m_sequenceShuffling(false), m_noiseDeviation(0)
 {
     if ((targetClasses == nullptr) == (targets == nullptr))
         throw std::runtime_error("DataSet needs exactly one of target classes / target patterns");
@@ -46,6 +74,7 @@ DataSet::DataSet(bl_ctx *ctx, int numSeqs, const int *seqLengths, int P, int O, 
         while (seqLength > 0) {                                                   // DataSet.cpp:527-542
             sequence_t seq;
             seq.originalSeqIdx = k;
+            seq.sourceSeq = i;
             if (truncSeqLength > 0 && seqLength > 1.5 * truncSeqLength)
                 seq.length = std::min(truncSeqLength, seqLength);
             else
@@ -70,13 +99,62 @@ DataSet::DataSet(bl_ctx *ctx, int numSeqs, const int *seqLengths, int P, int O, 
         std::sort(m_sequences.begin(), m_sequences.end(), comp_seqs);             // DataSet.cpp:603-605
 }
 
+DataSet::~DataSet()
+{
+    if (m_pending.valid()) m_pending.wait();
+}
+
+void DataSet::setSequenceTags(const std::vector<std::string> &tags)
+{
+    for (sequence_t &s : m_sequences)
+        if (s.sourceSeq < (int)tags.size()) s.seqTag = tags[s.sourceSeq];
+}
+
+void DataSet::setShuffling(bool fractionShuffling, bool sequenceShuffling, unsigned seed)
+{
+    m_fractionShuffling = fractionShuffling; m_sequenceShuffling = sequenceShuffling;
+    m_shuffleGen.seed(seed);
+}
+
+void DataSet::setInputNoise(real_t sigma, unsigned seed)
+{
+    m_noiseDeviation = sigma;
+    m_noiseGen.seed(seed + 7919u * (unsigned)m_rank);                             // independent noise per rank
+}
+
+void DataSet::shuffleSequences()
+{
+    std::shuffle(m_sequences.begin(), m_sequences.end(), m_shuffleGen);           // DataSet.cpp:225-229
+}
+
+void DataSet::shuffleFractions()
+{
+    // blocks of one GLOBAL fraction (S per rank x world) keep their members, the blocks are permuted (DataSet.cpp:231-246)
+    const size_t gs = (size_t)m_parallelSequences * m_world;
+    std::vector<std::vector<sequence_t>> fractions;
+    for (size_t i = 0; i < m_sequences.size(); ++i) {
+        if (i % gs == 0) fractions.resize(fractions.size() + 1);
+        fractions.back().push_back(m_sequences[i]);
+    }
+    std::shuffle(fractions.begin(), fractions.end(), m_shuffleGen);
+    m_sequences.clear();
+    for (const auto &f : fractions) m_sequences.insert(m_sequences.end(), f.begin(), f.end());
+}
+
+std::shared_ptr<DataSetFraction> DataSet::makeFirstFraction()
+{
+    if (m_sequenceShuffling) shuffleSequences();                                  // DataSet.cpp:416-426
+    if (m_fractionShuffling) shuffleFractions();
+    return makeFraction(0);
+}
+
 int DataSet::numFractions() const
 {
     const int gs = m_parallelSequences * m_world;
     return ((int)m_sequences.size() + gs - 1) / gs;
 }
 
-std::shared_ptr<DataSetFraction> DataSet::makeFraction(int firstSeqIdx) const
+std::shared_ptr<DataSetFraction> DataSet::makeFraction(int firstSeqIdx)
 {
     const int S = m_parallelSequences, P = m_inputPatternSize, O = m_outputPatternSize;
     std::shared_ptr<DataSetFraction> frac(new DataSetFraction);
@@ -99,11 +177,11 @@ std::shared_ptr<DataSetFraction> DataSet::makeFraction(int firstSeqIdx) const
     }
     if (frac->m_seqInfo.empty()) { frac->m_maxSeqLength = 0; frac->m_minSeqLength = 0; return frac; }   // empty shard
 
-    const size_t slots = (size_t)frac->m_maxSeqLength * S;
-    frac->m_inputs.resize(m_ctx, slots * P, 0);
-    frac->m_patTypes.resize(m_ctx, slots, PATTYPE_NONE);
-    if (m_isClassificationData) frac->m_targetClasses.resize(m_ctx, slots, -1);
-    else frac->m_outputs.resize(m_ctx, slots * O, 0);
+    const size_t slots = (size_t)frac->m_maxSeqLength * S, maxSlots = (size_t)m_maxSeqLength * S;
+    frac->m_inputs.resize(m_ctx, slots * P, 0, maxSlots * P);
+    frac->m_patTypes.resize(m_ctx, slots, PATTYPE_NONE, maxSlots);
+    if (m_isClassificationData) frac->m_targetClasses.resize(m_ctx, slots, -1, maxSlots);
+    else frac->m_outputs.resize(m_ctx, slots * O, 0, maxSlots * O);
 
     for (int i = 0; i < S; ++i) {
         if (first + i >= (int)m_sequences.size()) continue;
@@ -118,16 +196,34 @@ std::shared_ptr<DataSetFraction> DataSet::makeFraction(int firstSeqIdx) const
             frac->m_patTypes[slot] = (t == 0) ? PATTYPE_FIRST : (t == seq.length - 1) ? PATTYPE_LAST : PATTYPE_NORMAL;   // :397-406
         }
     }
+    if (m_noiseDeviation > 0) {                                                   // DataSet.cpp:250-266, 347
+        std::normal_distribution<real_t> dist((real_t)0, m_noiseDeviation);
+        for (int i = 0; i < S; ++i) {
+            if (first + i >= (int)m_sequences.size()) continue;
+            for (int t = 0; t < m_sequences[first + i].length; ++t) {
+                real_t *x = frac->m_inputs.data() + ((size_t)t * S + i) * P;
+                for (int p = 0; p < P; ++p) x[p] += dist(m_noiseGen);
+            }
+        }
+    }
     return frac;
 }
 
 std::shared_ptr<DataSetFraction> DataSet::getNextFraction()
 {
-    if (m_curFirstSeqIdx == -1) m_curFirstSeqIdx = 0;
+    const int gs = m_parallelSequences * m_world;
+    if (m_curFirstSeqIdx == -1) {
+        m_pending = std::async(std::launch::async, &DataSet::makeFirstFraction, this);
+        m_curFirstSeqIdx = 0;
+    }
     std::shared_ptr<DataSetFraction> frac;
     if (m_curFirstSeqIdx < (int)m_sequences.size()) {
-        frac = makeFraction(m_curFirstSeqIdx);
-        m_curFirstSeqIdx += m_parallelSequences * m_world;
+        frac = m_pending.get();
+        m_curFirstSeqIdx += gs;
+        if (m_curFirstSeqIdx < (int)m_sequences.size())
+            m_pending = std::async(std::launch::async, &DataSet::makeFraction, this, m_curFirstSeqIdx);
+        else
+            m_pending = std::async(std::launch::async, &DataSet::makeFirstFraction, this);    // next epoch's first fraction
     } else {
         m_curFirstSeqIdx = 0;                                                     // DataSet.cpp:662-664
     }

@@ -1,6 +1,7 @@
 // A fraction (minibatch) of parallel sequences in the reference's packing: slot n = t*S + s, features fastest
 // (data_sets/DataSetFraction.hpp:38-143; filled by data_sets::DataSet, DataSet.cpp:300-414).
 #pragma once
+#include <algorithm>
 #include <string>
 #include <vector>
 #include "Types.hpp"
@@ -19,15 +20,26 @@ public:
         std::string seqTag;
     };
 
-    // host buffers; pinned when the fraction was built with a device context (async H2D from the prefetch thread)
+    // host buffers; pinned when the fraction was built with a device context.  Pinned blocks come from a process-wide
+    // pool (cudaMallocHost / cudaFreeHost cost milliseconds and cudaFreeHost synchronises the device): a block goes back
+    // to the pool when its fraction dies.  That is safe because NeuralNetwork::calculateError() reads the error back
+    // (a stream synchronisation after the H2D copies of loadSequences) before a training step returns.
+    struct PinnedPool {
+        static void *get(bl_ctx *ctx, size_t bytes, size_t *capacity);
+        static void put(void *ptr, size_t capacity);
+    };
     template <typename T>
     struct HostBuffer {
-        T *ptr = nullptr; size_t n = 0; bl_ctx *ctx = nullptr; std::vector<T> pageable;
-        ~HostBuffer() { if (ctx && ptr) bl_free_host(ctx, ptr); }
-        void resize(bl_ctx *c, size_t count, T fill)
+        T *ptr = nullptr; size_t n = 0, cap = 0; bl_ctx *ctx = nullptr; std::vector<T> pageable;
+        HostBuffer() {}
+        HostBuffer(const HostBuffer &) = delete;
+        HostBuffer &operator=(const HostBuffer &) = delete;
+        ~HostBuffer() { if (ctx && ptr) PinnedPool::put(ptr, cap); }
+        // reserve >= count: blocks of one data set all have the capacity of its largest fraction, so they are interchangeable
+        void resize(bl_ctx *c, size_t count, T fill, size_t reserve = 0)
         {
             n = count; ctx = c;
-            if (c) { device::check(c, bl_malloc_host(c, (void **)&ptr, count * sizeof(T))); for (size_t i = 0; i < count; ++i) ptr[i] = fill; }
+            if (c) { ptr = (T *)PinnedPool::get(c, std::max(count, reserve) * sizeof(T), &cap); std::fill(ptr, ptr + count, fill); }
             else { pageable.assign(count, fill); ptr = pageable.data(); }
         }
         const T *data() const { return ptr; }

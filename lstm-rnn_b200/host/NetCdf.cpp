@@ -111,7 +111,8 @@ std::unique_ptr<DataSet> loadNetCdfDataSet(bl_ctx *ctx, const std::vector<std::s
 {
     if (fraction <= 0 || fraction > 1) throw std::runtime_error("Invalid fraction");
     std::vector<int> seqLengths, classes;
-    std::vector<float> inputs, targets;
+    std::vector<float> inputs, targets, means, stdevs;
+    std::vector<std::string> tags;
     bool first = true, isClassification = false;
     int P = 0, O = 0;
     for (const std::string &path : ncfiles) {
@@ -132,15 +133,29 @@ std::unique_ptr<DataSet> loadNetCdfDataSet(bl_ctx *ctx, const std::vector<std::s
         const std::vector<int> lens = nc.readInts("seqLengths");
         size_t frames = 0;
         for (int i = 0; i < nSeq; ++i) { seqLengths.push_back(lens[i]); frames += (size_t)lens[i]; }
+        const int tagLen = nc.dimension("maxSeqTagLength");
+        const std::vector<char> tagChars = nc.readChars("seqTags");
+        for (int i = 0; i < nSeq; ++i) {                                                                          // DataSet.cpp:525
+            const char *t = tagChars.data() + (size_t)i * tagLen;
+            size_t n = 0; while (n < (size_t)tagLen && t[n]) ++n;
+            tags.emplace_back(t, n);
+        }
+        if (first && !cls) {                                                                                      // DataSet.cpp:572-582
+            if (nc.hasVariable("outputMeans") && nc.hasVariable("outputStdevs")) { means = nc.readFloats("outputMeans"); stdevs = nc.readFloats("outputStdevs"); }
+        }
         const std::vector<float> in = nc.readFloats("inputs");
         inputs.insert(inputs.end(), in.begin(), in.begin() + frames * P);
         if (cls) { const std::vector<int> tc = nc.readInts("targetClasses"); classes.insert(classes.end(), tc.begin(), tc.begin() + frames); }
         else { const std::vector<float> tp = nc.readFloats("targetPatterns"); targets.insert(targets.end(), tp.begin(), tp.begin() + frames * O); }
         first = false;
     }
-    return std::unique_ptr<DataSet>(new DataSet(ctx, (int)seqLengths.size(), seqLengths.data(), P, O, inputs.data(),
-                                                isClassification ? classes.data() : nullptr, isClassification ? nullptr : targets.data(),
-                                                parSeq, truncSeqLength, trainingMode, rank, world));
+    std::unique_ptr<DataSet> ds(new DataSet(ctx, (int)seqLengths.size(), seqLengths.data(), P, O, inputs.data(),
+                                            isClassification ? classes.data() : nullptr, isClassification ? nullptr : targets.data(),
+                                            parSeq, truncSeqLength, trainingMode, rank, world));
+    ds->setSequenceTags(tags);
+    if ((int)means.size() != O || (int)stdevs.size() != O) { means.assign(O, 0.0f); stdevs.assign(O, 1.0f); }
+    ds->setOutputStatistics(means, stdevs);
+    return ds;
 }
 
 } // namespace data_sets

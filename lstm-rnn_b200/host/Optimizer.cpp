@@ -1,4 +1,7 @@
 #include "Optimizer.hpp"
+#include <cmath>
+#include <limits>
+#include <stdexcept>
 
 using device::check;
 
@@ -6,7 +9,11 @@ namespace optimizers {
 
 SteepestDescentOptimizer::SteepestDescentOptimizer(NeuralNetwork &nn, real_t learningRate, real_t momentum, bool hybridOnlineBatch)
     : m_nn(nn), m_learningRate(learningRate), m_momentum(momentum), m_hybridOnlineBatch(hybridOnlineBatch)
+    , m_lowestValidationError(std::numeric_limits<real_t>::max())
+    , m_curTrainingError(std::numeric_limits<real_t>::max()), m_curValidationError(std::numeric_limits<real_t>::max())
+    , m_curTestError(std::numeric_limits<real_t>::max())
 {
+    m_stats.allocate(nn.ctx(), 4, true);
     for (const auto &layer : nn.layers()) {
         layers::TrainableLayer *tl = dynamic_cast<layers::TrainableLayer *>(layer.get());
         const size_t n = tl ? tl->weights().size() : 0;
@@ -81,9 +88,88 @@ real_t SteepestDescentOptimizer::processDataSet(data_sets::DataSet &ds, bool cal
     }
     if (calcWeightUpdates && !m_hybridOnlineBatch) updateWeights();
     check(m_nn.ctx(), bl_sync(m_nn.ctx()));
+    if (m_nn.communicator()) {
+        // every rank saw only its columns of each fraction: sum the statistics (the count is split so that fp32 stays exact)
+        const long missed = std::lround((double)*classError);
+        real_t st[4] = {error, (real_t)(missed / 4096), (real_t)(missed % 4096), 0};
+        long base = 0;
+        if (ds.totalTimesteps() > 0) base = (long)ds.totalTimesteps();
+        m_stats.fromHost(st, 4);
+        check(m_nn.ctx(), bl_allreduce_sum_f32(m_nn.communicator(), m_stats.data(), 4));
+        check(m_nn.ctx(), bl_comm_join(m_nn.communicator()));
+        m_stats.toHost(st, 4);
+        int world = 1;
+        bl_comm_info(m_nn.communicator(), nullptr, &world);
+        error = st[0];
+        // each rank started from totalTimesteps and subtracted its own correct count
+        *classError = (real_t)((double)st[1] * 4096.0 + (double)st[2] - (double)(world - 1) * (double)base);
+    }
     error /= ds.totalSequences();
     *classError /= (real_t)ds.totalTimesteps();
     return error;
+}
+
+void SteepestDescentOptimizer::setDataSets(data_sets::DataSet *trainingSet, data_sets::DataSet *validationSet, data_sets::DataSet *testSet,
+                                           int maxEpochs, int maxEpochsNoBest, int validateEvery, int testEvery)
+{
+    m_trainingSet = trainingSet; m_validationSet = validationSet; m_testSet = testSet;
+    m_maxEpochs = maxEpochs; m_maxEpochsNoBest = maxEpochsNoBest; m_validateEvery = validateEvery; m_testEvery = testEvery;
+}
+
+void SteepestDescentOptimizer::storeWeights()
+{
+    bl_ctx *ctx = m_nn.ctx();
+    if (m_bestWeights.empty())
+        for (const auto &layer : m_nn.layers()) {
+            layers::TrainableLayer *tl = dynamic_cast<layers::TrainableLayer *>(layer.get());
+            m_bestWeights.emplace_back(new device::real_vector(ctx, tl ? tl->weights().size() : 0, false));
+        }
+    for (size_t i = 0; i < m_nn.layers().size(); ++i) {
+        layers::TrainableLayer *tl = dynamic_cast<layers::TrainableLayer *>(m_nn.layers()[i].get());
+        if (tl) check(ctx, bl_memcpy_d2d(ctx, m_bestWeights[i]->data(), tl->weights().data(), tl->weights().size() * sizeof(real_t)));
+    }
+}
+
+void SteepestDescentOptimizer::restoreWeights()
+{
+    bl_ctx *ctx = m_nn.ctx();
+    if (m_bestWeights.empty()) return;
+    for (size_t i = 0; i < m_nn.layers().size(); ++i) {
+        layers::TrainableLayer *tl = dynamic_cast<layers::TrainableLayer *>(m_nn.layers()[i].get());
+        if (tl) check(ctx, bl_memcpy_d2d(ctx, tl->weights().data(), m_bestWeights[i]->data(), tl->weights().size() * sizeof(real_t)));
+    }
+    check(ctx, bl_sync(ctx));
+}
+
+bool SteepestDescentOptimizer::train()
+{
+    if (!m_trainingSet) throw std::runtime_error("Optimizer::train: no training set");
+    const bool haveVal = m_validationSet && !m_validationSet->empty();
+    const bool haveTest = m_testSet && !m_testSet->empty();
+    if (!m_finished) {
+        ++m_curEpoch;
+        m_curTrainingError = processDataSet(*m_trainingSet, true, &m_curTrainingClassError);
+        if (haveVal && m_curEpoch % m_validateEvery == 0) {
+            m_curValidationError = processDataSet(*m_validationSet, false, &m_curValidationClassError);
+            if (m_curValidationError < m_lowestValidationError) {
+                m_lowestValidationError = m_curValidationError;
+                m_epochsSinceLowestError = 0;
+                storeWeights();
+            } else {
+                m_epochsSinceLowestError += m_validateEvery;
+            }
+        } else if (!haveVal) {
+            m_epochsSinceLowestError = 0;
+            storeWeights();
+        }
+        if (haveTest && m_curEpoch % m_testEvery == 0)
+            m_curTestError = processDataSet(*m_testSet, false, &m_curTestClassError);
+        if (m_epochsSinceLowestError >= m_maxEpochsNoBest || (m_maxEpochs >= 0 && m_curEpoch >= m_maxEpochs)) {
+            restoreWeights();
+            m_finished = true;
+        }
+    }
+    return m_finished;
 }
 
 std::vector<std::vector<real_t>> SteepestDescentOptimizer::weightDeltasToHost() const

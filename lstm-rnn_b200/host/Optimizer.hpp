@@ -28,6 +28,24 @@ public:
     // applies the accumulated updates (batch mode) -- _updateWeights(), SteepestDescentOptimizer.cu:67-94
     void updateWeights();
 
+    // ---- epoch loop with early stopping (Optimizer.cu:283-324) ----
+    // data sets may be null / empty; maxEpochs < 0 = unlimited
+    void setDataSets(data_sets::DataSet *trainingSet, data_sets::DataSet *validationSet, data_sets::DataSet *testSet,
+                     int maxEpochs, int maxEpochsNoBest, int validateEvery, int testEvery);
+    // trains one epoch, evaluates validation / test sets when due, keeps the best weights; true once training is finished
+    // (the best weights are restored then)
+    bool train();
+    bool finished() const { return m_finished; }
+    int currentEpoch() const { return m_curEpoch; }
+    real_t lowestValidationError() const { return m_lowestValidationError; }
+    int epochsSinceLowestValidationError() const { return m_epochsSinceLowestError; }
+    real_t curTrainingError() const { return m_curTrainingError; }
+    real_t curValidationError() const { return m_curValidationError; }
+    real_t curTestError() const { return m_curTestError; }
+    real_t curTrainingClassError() const { return m_curTrainingClassError; }
+    real_t curValidationClassError() const { return m_curValidationClassError; }
+    real_t curTestClassError() const { return m_curTestClassError; }
+
     real_t learningRate() const { return m_learningRate; }
     void setLearningRate(real_t lr) { m_learningRate = lr; }
     std::vector<std::vector<real_t>> weightDeltasToHost() const;
@@ -38,6 +56,19 @@ private:
     bool m_hybridOnlineBatch;
     std::vector<std::unique_ptr<device::real_vector>> m_curWeightUpdates;   // batch mode accumulators
     std::vector<std::unique_ptr<device::real_vector>> m_weightDeltas;       // momentum state
+    std::vector<std::unique_ptr<device::real_vector>> m_bestWeights;        // Optimizer.cu:106-127
+    device::real_vector m_stats;                                            // {error, correct/4096, correct%4096} summed over ranks
+
+    data_sets::DataSet *m_trainingSet = nullptr, *m_validationSet = nullptr, *m_testSet = nullptr;
+    int m_maxEpochs = -1, m_maxEpochsNoBest = 20, m_validateEvery = 1, m_testEvery = 1;
+    bool m_finished = false;
+    int m_curEpoch = 0, m_epochsSinceLowestError = 0;
+    real_t m_lowestValidationError;
+    real_t m_curTrainingError, m_curValidationError, m_curTestError;
+    real_t m_curTrainingClassError = 0, m_curValidationClassError = 0, m_curTestClassError = 0;
+
+    void storeWeights();
+    void restoreWeights();
 };
 
 } // namespace optimizers

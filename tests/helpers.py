@@ -112,3 +112,39 @@ def compare_to_golden(g, net, layers, err, correct, tol, exact=False):
             cmp("output_errors%d" % i, net.get_output_errors(i), g["output_errors%d" % i])
             cmp("weight_updates%d" % i, net.get_weight_updates(i), g["weight_updates%d" % i])
     return worst
+
+
+def write_nc(path, xs, cs=None, ts=None, labels=0, version=1, extra=True):
+    """Writes sequences in the reference's NetCDF schema (data_sets/DataSet.cpp:486-583) with scipy's classic-format writer."""
+    from scipy.io import netcdf_file
+    lens = np.array([len(x) for x in xs], np.int32)
+    f = netcdf_file(path, "w", version=version)
+    f.createDimension("numSeqs", len(xs))
+    f.createDimension("numTimesteps", int(lens.sum()))
+    f.createDimension("inputPattSize", xs[0].shape[1])
+    f.createDimension("maxSeqTagLength", 12)
+    if cs is not None:
+        f.createDimension("numLabels", labels)
+    else:
+        f.createDimension("targetPattSize", ts[0].shape[1])
+    if extra:                                                        # variables the reader must skip (as in the shipped example)
+        f.createDimension("maxLabelLength", 5)
+        f.history = "synthetic"
+        v = f.createVariable("labelIds", ">i2", ("maxLabelLength",))
+        v[:] = np.arange(5)
+    v = f.createVariable("seqTags", "S1", ("numSeqs", "maxSeqTagLength"))
+    for i in range(len(xs)):
+        tag = ("seq%03d" % i).encode().ljust(12, b"\0")
+        v[i, :] = np.frombuffer(tag, "S1")
+    v = f.createVariable("seqLengths", ">i4", ("numSeqs",))
+    v.units = "frames"
+    v[:] = lens
+    v = f.createVariable("inputs", ">f4", ("numTimesteps", "inputPattSize"))
+    v[:] = np.concatenate(xs, 0)
+    if cs is not None:
+        v = f.createVariable("targetClasses", ">i4", ("numTimesteps",))
+        v[:] = np.concatenate(cs)
+    else:
+        v = f.createVariable("targetPatterns", ">f4", ("numTimesteps", "targetPattSize"))
+        v[:] = np.concatenate(ts, 0)
+    f.close()

@@ -1,0 +1,188 @@
+"""The command line trainer (lstm-rnn_b200/currennt_b200, mirror of currennt/src/main.cpp) end to end on the GPU:
+.nc files + network.jsn + reference option names in, epoch table + trained_network.jsn / ff_output.csv out, checked
+against the oracle replaying the same epochs."""
+import json
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+sys.path.insert(0, os.path.join(os.path.dirname(__file__), "..", "lstm-rnn_b200", "python"))
+sys.path.insert(0, os.path.dirname(__file__))
+import synth  # noqa: E402
+from helpers import rel_err, write_nc  # noqa: E402
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.join(os.path.dirname(__file__), "..")
+EXE = os.path.join(ROOT, "lstm-rnn_b200", "currennt_b200")
+
+
+def _with_weights(net_json, weights):
+    """network.jsn with a "weights" section (input | bias | internal per layer, TrainableLayer.cu:211-238), full precision."""
+    doc = json.loads(net_json) if isinstance(net_json, str) else json.loads(json.dumps(net_json))
+    sec = {}
+    for i, layer in enumerate(doc["layers"]):
+        w = weights[i]
+        if not len(w):
+            continue
+        P, L = doc["layers"][i - 1]["size"], layer["size"]
+        if layer["type"] in ("lstm", "blstm"):
+            n_in, n_b = 4 * L * P, 4 * L
+        else:
+            n_in, n_b = L * P, L
+        sec[layer["name"]] = {"input": [float(x) for x in w[:n_in]], "bias": [float(x) for x in w[n_in:n_in + n_b]],
+                              "internal": [float(x) for x in w[n_in + n_b:]]}
+    doc["weights"] = sec
+    return doc
+
+
+def _saved_weights(path):
+    doc = json.load(open(path))
+    out = {}
+    for layer in doc["layers"]:
+        if layer["name"] in doc.get("weights", {}):
+            w = doc["weights"][layer["name"]]
+            out[layer["name"]] = np.array(list(w["input"]) + list(w["bias"]) + list(w["internal"]), np.float32)
+    return doc, out
+
+
+def _run(args, cwd, env=None):
+    r = subprocess.run([EXE] + args, cwd=cwd, capture_output=True, text=True, timeout=600, env=env)
+    assert r.returncode == 0, r.stdout + r.stderr
+    return r.stdout
+
+
+def _epoch_rows(stdout):
+    rows = []
+    for line in stdout.splitlines():
+        m = re.match(r"\s+(\d+) \|\s+[\d.]+ \|\s*([\d.]+)%\s+([\d.]+) \|(?:\s*([\d.]+)%\s+([\d.]+) \|)?", line)
+        if m:
+            rows.append([float(x) if x is not None else None for x in m.groups()])
+    return rows
+
+
+def _setup(tmp_path, n_train=30, n_val=7):
+    cfg = synth.config("C1")
+    rng = np.random.default_rng(5)
+    tr_len = rng.permutation(np.arange(10, 10 + n_train))               # distinct lengths: the sort by length has no ties
+    va_len = rng.integers(8, 30, n_val)
+    xs, cs, _ = synth.make_sequences(tr_len, 39, 1, classes=51)
+    vx, vc, _ = synth.make_sequences(va_len, 39, 2, classes=51)
+    weights = synth.init_weights(cfg["net"], 3)
+    write_nc(str(tmp_path / "train.nc"), xs, cs, labels=51)
+    write_nc(str(tmp_path / "val.nc"), vx, vc, labels=51)
+    json.dump(_with_weights(cfg["net"], weights), open(tmp_path / "network.jsn", "w"))
+    return cfg, (xs, cs), (vx, vc), weights
+
+
+def _oracle_epochs(oracle, cfg, train, val, weights, S, lr, mom, epochs, world=1):
+    xs, cs = train
+    order = np.argsort([len(x) for x in xs], kind="stable")
+    xs, cs = [xs[i] for i in order], [cs[i] for i in order]
+    vx, vc = val
+    maxT = max(max(len(x) for x in xs), max(len(x) for x in vx))
+    net = oracle.OracleNet(cfg["net"], S * world, maxT)
+    for i, w in enumerate(weights):
+        if len(w):
+            net.set_weights(i, w)
+    deltas = [np.zeros_like(w) for w in weights]
+    rows = []
+    for _ in range(epochs):
+        e = c = 0
+        for first in range(0, len(xs), S * world):
+            f = oracle.make_fraction(xs, S * world, first, seq_classes=cs, O=51)
+            net.load_fraction(f); net.forward(); e += net.calculate_error(); c += net.count_correct(); net.backward()
+            net.sgd_update(deltas, lr, mom)
+        ve = vcor = 0
+        for first in range(0, len(vx), S * world):
+            f = oracle.make_fraction(vx, S * world, first, seq_classes=vc, O=51)
+            net.load_fraction(f); net.forward(); ve += net.calculate_error(); vcor += net.count_correct()
+        rows.append((100 * (1 - c / sum(len(x) for x in xs)), e / len(xs), 100 * (1 - vcor / sum(len(x) for x in vx)), ve / len(vx)))
+    return net, rows
+
+
+def test_cli_training_matches_oracle(oracle, tmp_path):
+    cfg, train, val, weights = _setup(tmp_path)
+    (tmp_path / "config.cfg").write_text(
+        "# options file in the reference's format\nnetwork = network.jsn\ntrain = true\ntrain_file = train.nc\nval_file = val.nc\n"
+        "stochastic = true\nparallel_sequences = 10\nlearning_rate = 1e-3\nmomentum = 0.9\nmax_epochs = 3\n")
+    out = _run(["--options_file", "config.cfg", "--save_network", "trained.jsn", "--random_seed", "7"], str(tmp_path))
+    assert "Maximum number of training epochs reached" in out and "Storing the trained network in 'trained.jsn'... done." in out
+    rows = _epoch_rows(out)
+    net, want = _oracle_epochs(oracle, cfg, train, val, weights, 10, 1e-3, 0.9, 3)
+    assert len(rows) == 3
+    for got, w in zip(rows, want):
+        assert got[0] == 1 + want.index(w)
+        assert abs(got[1] - w[0]) <= 0.011 and abs(got[2] - w[1]) <= 0.0011          # table prints %6.2lf%% / %10.3lf
+        assert abs(got[3] - w[2]) <= 0.011 and abs(got[4] - w[3]) <= 0.0011
+    doc, saved = _saved_weights(tmp_path / "trained.jsn")
+    # the network with the lowest validation error is the one stored (Optimizer.cu:296-317); with a falling validation
+    # error that is the last epoch, which the oracle holds
+    assert [r[3] for r in want] == sorted([r[3] for r in want], reverse=True)
+    for i, layer in enumerate(doc["layers"]):
+        if layer["name"] in saved:
+            assert rel_err(saved[layer["name"]], net.get_weights(i)) <= 1e-5       # "%g"-like export precision + strict fp32 parity
+
+
+def test_cli_forward_pass_single_csv(oracle, tmp_path):
+    cfg, train, val, weights = _setup(tmp_path)
+    out = _run(["--network", "network.jsn", "--ff_input_file", "val.nc", "--ff_output_file", "ff.csv", "--parallel_sequences", "3",
+                "--revert_std", "false"], str(tmp_path))
+    assert "Computing outputs for data fraction 3... done." in out
+    vx, vc = val
+    net = oracle.OracleNet(cfg["net"], 3, max(len(x) for x in vx))
+    for i, w in enumerate(weights):
+        if len(w):
+            net.set_weights(i, w)
+    lines = open(tmp_path / "ff.csv").read().splitlines()
+    assert len(lines) == len(vx)
+    k = 0
+    for first in range(0, len(vx), 3):
+        f = oracle.make_fraction(vx, 3, first, seq_classes=vc, O=51)
+        net.load_fraction(f); net.forward()
+        y = net.get_outputs(len(cfg["net"]["layers"]) - 2).reshape(f.T, 3, 51)
+        for s in range(f.num_seqs):
+            parts = lines[k].split(";")
+            assert parts[0] == "seq%03d" % k                                        # tags come from the seqTags variable
+            got = np.array([float(v) for v in parts[1:]], np.float32).reshape(-1, 51)
+            assert got.shape[0] == len(vx[k])
+            assert np.allclose(got, y[:len(vx[k]), s], rtol=2e-5, atol=1e-9)        # ostream prints 6 significant digits
+            k += 1
+
+
+def test_cli_rejects_what_it_does_not_implement(tmp_path):
+    r = subprocess.run([EXE, "--cuda", "false"], capture_output=True, text=True)
+    assert r.returncode == 2 and "no CPU path" in r.stdout
+    r = subprocess.run([EXE, "--no_such_option", "1"], capture_output=True, text=True)
+    assert r.returncode == 1 and "unrecognised option" in r.stderr
+    r = subprocess.run([EXE, "--train", "true", "--train_file", "missing.nc", "--network", "missing.jsn"], capture_output=True, text=True)
+    assert r.returncode == 2 and "FAILED" in r.stdout
+
+
+def test_cli_data_parallel_two_processes(oracle, tmp_path):
+    """Two processes x S=5 train like one process x S=10 (sum of gradients over the global fraction)."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    cfg, train, val, weights = _setup(tmp_path)
+    args = ["--network", "network.jsn", "--train", "true", "--train_file", "train.nc", "--val_file", "val.nc", "--stochastic", "true",
+            "--parallel_sequences", "5", "--learning_rate", "1e-3", "--momentum", "0.9", "--max_epochs", "2", "--save_network", "dp.jsn"]
+    procs = []
+    for r in range(2):
+        env = dict(os.environ, RANK=str(r), WORLD_SIZE="2", LOCAL_RANK=str(r), MASTER_ADDR="127.0.0.1", MASTER_PORT="29611")
+        procs.append(subprocess.Popen([EXE] + args, cwd=str(tmp_path), stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, env=env))
+    outs = [p.communicate(timeout=600)[0] for p in procs]
+    assert all(p.returncode == 0 for p in procs), outs
+    rows = _epoch_rows(outs[0])
+    net, want = _oracle_epochs(oracle, cfg, train, val, weights, 5, 1e-3, 0.9, 2, world=2)
+    assert len(rows) == 2 and not _epoch_rows(outs[1])                                # only rank 0 prints
+    for got, w in zip(rows, want):
+        assert abs(got[1] - w[0]) <= 0.011 and abs(got[2] - w[1]) <= 0.0011
+        assert abs(got[3] - w[2]) <= 0.011 and abs(got[4] - w[3]) <= 0.0011
+    doc, saved = _saved_weights(tmp_path / "dp.jsn")
+    for i, layer in enumerate(doc["layers"]):
+        if layer["name"] in saved:
+            assert rel_err(saved[layer["name"]], net.get_weights(i)) <= 1e-5

@@ -9,42 +9,11 @@ import numpy as np
 import pytest
 from scipy.io import netcdf_file
 
+sys.path.insert(0, os.path.dirname(__file__))
+
 sys.path.insert(0, os.path.join(os.path.dirname(__file__), "..", "lstm-rnn_b200", "python"))
 import currennt_b200 as cb  # noqa: E402
-
-
-def _write_nc(path, xs, cs=None, ts=None, labels=0, version=1, extra=True):
-    lens = np.array([len(x) for x in xs], np.int32)
-    f = netcdf_file(path, "w", version=version)
-    f.createDimension("numSeqs", len(xs))
-    f.createDimension("numTimesteps", int(lens.sum()))
-    f.createDimension("inputPattSize", xs[0].shape[1])
-    f.createDimension("maxSeqTagLength", 12)
-    if cs is not None:
-        f.createDimension("numLabels", labels)
-    else:
-        f.createDimension("targetPattSize", ts[0].shape[1])
-    if extra:                                                        # variables the reader must skip (as in the shipped example)
-        f.createDimension("maxLabelLength", 5)
-        f.history = "synthetic"
-        v = f.createVariable("labelIds", ">i2", ("maxLabelLength",))
-        v[:] = np.arange(5)
-    v = f.createVariable("seqTags", "S1", ("numSeqs", "maxSeqTagLength"))
-    for i in range(len(xs)):
-        tag = ("seq%03d" % i).encode().ljust(12, b"\0")
-        v[i, :] = np.frombuffer(tag, "S1")
-    v = f.createVariable("seqLengths", ">i4", ("numSeqs",))
-    v.units = "frames"
-    v[:] = lens
-    v = f.createVariable("inputs", ">f4", ("numTimesteps", "inputPattSize"))
-    v[:] = np.concatenate(xs, 0)
-    if cs is not None:
-        v = f.createVariable("targetClasses", ">i4", ("numTimesteps",))
-        v[:] = np.concatenate(cs)
-    else:
-        v = f.createVariable("targetPatterns", ">f4", ("numTimesteps", "targetPattSize"))
-        v[:] = np.concatenate(ts, 0)
-    f.close()
+from helpers import write_nc as _write_nc  # noqa: E402
 
 
 def _data(n, P, O, classification, seed=3):
