@@ -143,7 +143,7 @@ def test_cli_forward_pass_single_csv(oracle, tmp_path):
     for first in range(0, len(vx), 3):
         f = oracle.make_fraction(vx, 3, first, seq_classes=vc, O=51)
         net.load_fraction(f); net.forward()
-        y = net.get_outputs(len(cfg["net"]["layers"]) - 2).reshape(f.T, 3, 51)
+        y = net.get_outputs(len(json.loads(cfg["net"])["layers"]) - 2).reshape(f.T, 3, 51)
         for s in range(f.num_seqs):
             parts = lines[k].split(";")
             assert parts[0] == "seq%03d" % k                                        # tags come from the seqTags variable
