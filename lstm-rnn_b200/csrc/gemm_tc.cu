@@ -2,8 +2,11 @@
 // input-to-gate projection, input-error and weight-gradient GEMMs (reference: the cublasSgemm calls behind
 // helpers::Matrix, layers/LstmLayer.cu:774-784, 996-1006, 1038-1043; layers/FeedForwardLayer.cu:152, 196, 206).
 //
-// Kernel: C[M x N] (row-major, ldc) = A[M x K] * B[N x K]^T, both operands K-major fp32 in global memory.
-//   warp 0      TMA producer: cp.async.bulk.tensor 2D boxes (32 floats = 128 B along K) into 128B-swizzled shared tiles
+// Kernel: C[M x N] (row-major, ldc) = A[M x K] * B[N x K]^T on fp32 operands in global memory.  Either operand may be
+// K-major ([MN][K], K contiguous) or MN-major ([K][MN], MN contiguous -- the "transposed" view of the same row-major
+// matrix): tcgen05 reads both from 128B-swizzled shared tiles, so no operand is ever transposed in memory.
+//   warp 0      TMA producer: cp.async.bulk.tensor 2D boxes (32 floats = 128 B along the contiguous dimension) into
+//               128B-swizzled shared tiles; K-major: one [BM x 32] box, MN-major: BM/32 boxes of [32 k x 32 mn]
 //   warp 1      MMA issuer: one elected thread issues tcgen05.mma.cta_group::1.kind::tf32 (M=128, N=BN, K=8 per instruction),
 //               accumulating in TMEM (fp32); tcgen05.commit releases shared stages and signals the epilogue
 //   warp 2      TMEM allocation / deallocation
@@ -12,7 +15,7 @@
 //   BL_GEMM_FAST    one TF32 MMA per k-step (10-bit mantissa products, fp32 accumulate)          -> <= 2e-3 class
 //   BL_GEMM_STRICT  error-compensated 3xTF32: every operand is split in global memory into hi = tf32(x) and
 //                   lo = x - hi (exact), and the kernel accumulates hi*hi + hi*lo + lo*hi in TMEM       -> fp32 class
-// Operands that are not K-major / 16-byte aligned are first transposed into scratch (bandwidth-bound pass).
+// The only preparation pass is elementwise (split + re-pitch to 16-byte aligned rows); see tc_prepare.
 // Split-K (grid.z) with ordered partial-sum reduction keeps the result deterministic.
 #include "common.cuh"
 #include "gemm_tc.cuh"
@@ -28,7 +31,7 @@ struct GemmTcParams {
     CUtensorMap tmA, tmAlo, tmB, tmBlo;     // lo maps unused in fast mode
     float *C; int ldc;
     int M, N, K;
-    int a_k0, b_k0;                          // element offsets added to the K coordinate of the A / B boxes (time-shifted operands)
+    int a_mn, b_mn;                          // 1: operand is MN-major (tensor map dims {MN, K}), 0: K-major (dims {K, MN})
     int batches, mt_per_batch;               // grid.y = batches * mt_per_batch: batch b multiplies A rows [b*a_batch_rows, +M) by the same B
     int a_batch_rows; long long c_batch_stride;   // and writes its [M x N] block at C + b*c_batch_stride
     int kblocks_per_split;
@@ -73,20 +76,34 @@ __device__ __forceinline__ bool elect_one()
 // K-major, 128B-swizzled shared-memory matrix descriptor (cute::UMMA::SmemDescriptor, mma_sm100_desc.hpp):
 // start address >> 4 in [0,14), LBO (unused for one swizzle atom along K) in [16,30), SBO = 1024 B (8 rows x 128 B) >> 4 in [32,46),
 // version 1 in [46,48), layout type SWIZZLE_128B = 2 in [61,64)
-__device__ __forceinline__ uint64_t make_smem_desc(const void *smem_ptr)
+//
+// MN-major TF32 operands have ONE legal shared layout, SWIZZLE_128B_BASE32B (layout type 1; cutlass sm100_common.inl:92): 32-byte
+// chunks swizzled inside 128 B rows, repeating every 4 rows -- TMA's CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B.  Canonical layout in floats
+// ((4,8,m),(4,k)):((1,4,LBO),(32,SBO)) (mma_traits_sm100.hpp:72-75,175): an atom is 32 floats along MN x 4 k-rows of 128 B;
+// SBO = distance between successive groups of 4 k-rows (512 B: the rows of a box are consecutive), LBO = distance between successive
+// 32-float MN chunks (one [32 k x 128 B] box = 4096 B).
+__device__ __forceinline__ uint64_t make_smem_desc(const void *smem_ptr, bool mn_major)
 {
     uint64_t d = 0;
     d |= (uint64_t)((smem_u32(smem_ptr) & 0x3FFFF) >> 4);
-    d |= (uint64_t)(1024 >> 4) << 32;
-    d |= (uint64_t)1 << 46;
-    d |= (uint64_t)2 << 61;
+    if (mn_major) {
+        d |= (uint64_t)((TC_BK * 128) >> 4) << 16;
+        d |= (uint64_t)(512 >> 4) << 32;
+        d |= (uint64_t)1 << 46;
+        d |= (uint64_t)1 << 61;
+    } else {
+        d |= (uint64_t)(1024 >> 4) << 32;
+        d |= (uint64_t)1 << 46;
+        d |= (uint64_t)2 << 61;
+    }
     return d;
 }
 
-// instruction descriptor (cute::UMMA::InstrDescriptor): D fp32 [4,6)=1, A/B tf32 [7,10)=[10,13)=2, both K-major, N>>3 at [17,23), M>>4 at [24,29)
-__device__ __forceinline__ uint32_t make_idesc(int M, int N)
+// instruction descriptor (cute::UMMA::InstrDescriptor): D fp32 [4,6)=1, A/B tf32 [7,10)=[10,13)=2, A / B MN-major at bits 15 / 16,
+// N>>3 at [17,23), M>>4 at [24,29)
+__device__ __forceinline__ uint32_t make_idesc(int M, int N, int a_mn, int b_mn)
 {
-    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)a_mn << 15) | ((uint32_t)b_mn << 16) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
 __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate)
@@ -163,44 +180,55 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tf32_tcgen05_kernel(const 
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp == 0) {
-        // ===== TMA producer =====
-        if (elect_one()) {
-            for (int i = 0; i < nkb; ++i) {
-                const int s = i % STAGES, round = i / STAGES;
+        // ===== TMA producer: lane 0 owns the barriers, lanes 0..(loads-1) each issue one box =====
+        // load list of a stage: A hi chunks | B hi chunks | A lo chunks | B lo chunks  (K-major operand: 1 chunk, MN-major: tile/32 chunks)
+        const int nca = p.a_mn ? TC_BM / 32 : 1, ncb = p.b_mn ? BN / 32 : 1;
+        const int nload = (STRICT ? 2 : 1) * (nca + ncb);
+        int l = lane;
+        const bool is_lo = l >= nca + ncb; if (is_lo) l -= nca + ncb;
+        const bool is_b = l >= nca; const int chunk = is_b ? l - nca : l;
+        const CUtensorMap *map = is_b ? (is_lo ? &p.tmBlo : &p.tmB) : (is_lo ? &p.tmAlo : &p.tmA);
+        const int mn_major = is_b ? p.b_mn : p.a_mn;
+        const int mn = (is_b ? n0 : a_row0) + (mn_major ? chunk * 32 : 0);
+        const int dst_off = (is_lo ? A_BYTES + B_BYTES : 0) + (is_b ? A_BYTES : 0) + (mn_major ? chunk * TC_BK * 128 : 0);
+        for (int i = 0; i < nkb; ++i) {
+            const int s = i % STAGES, round = i / STAGES;
+            if (lane == 0) {
                 mbar_wait(&empty[s], (round & 1) ^ 1);                 // first pass over the ring succeeds immediately
-                uint8_t *st = smem + s * STAGE_BYTES;
                 mbar_expect_tx(&full[s], STAGE_BYTES);
+            }
+            __syncwarp();
+            if (lane < nload) {
                 const int kc = (kb_begin + i) * TC_BK;
-                tma_load_2d(st, &p.tmA, &full[s], kc + p.a_k0, a_row0);
-                tma_load_2d(st + A_BYTES, &p.tmB, &full[s], kc + p.b_k0, n0);
-                if (STRICT) {
-                    tma_load_2d(st + A_BYTES + B_BYTES, &p.tmAlo, &full[s], kc + p.a_k0, a_row0);
-                    tma_load_2d(st + 2 * A_BYTES + B_BYTES, &p.tmBlo, &full[s], kc + p.b_k0, n0);
-                }
+                uint8_t *dst = smem + s * STAGE_BYTES + dst_off;
+                if (mn_major) tma_load_2d(dst, map, &full[s], mn, kc);
+                else          tma_load_2d(dst, map, &full[s], kc, mn);
             }
         }
     } else if (warp == 1) {
         // ===== MMA issuer =====
-        const uint32_t idesc = make_idesc(TC_BM, BN);
+        const uint32_t idesc = make_idesc(TC_BM, BN, p.a_mn, p.b_mn);
+        const uint64_t a_step = (uint64_t)(((p.a_mn ? 1024 : TC_UMMA_K * 4)) >> 4), b_step = (uint64_t)(((p.b_mn ? 1024 : TC_UMMA_K * 4)) >> 4);
         for (int i = 0; i < nkb; ++i) {
             const int s = i % STAGES, round = i / STAGES;
             mbar_wait(&full[s], round & 1);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             if (elect_one()) {
                 const uint8_t *st = smem + s * STAGE_BYTES;
-                const uint64_t a_hi = make_smem_desc(st), b_hi = make_smem_desc(st + A_BYTES);
-                const uint64_t a_lo = make_smem_desc(st + A_BYTES + B_BYTES), b_lo = make_smem_desc(st + 2 * A_BYTES + B_BYTES);
+                const uint64_t a_hi = make_smem_desc(st, p.a_mn), b_hi = make_smem_desc(st + A_BYTES, p.b_mn);
+                const uint64_t a_lo = make_smem_desc(st + A_BYTES + B_BYTES, p.a_mn), b_lo = make_smem_desc(st + 2 * A_BYTES + B_BYTES, p.b_mn);
 #pragma unroll
                 for (int kk = 0; kk < TC_BK / TC_UMMA_K; ++kk) {
-                    const uint64_t adv = (uint64_t)((kk * TC_UMMA_K * 4) >> 4);      // advance the start address inside the swizzle atom
+                    // next 8 k: 32 B further inside the swizzle atom (K-major) or the next 8-row atom, 1024 B (MN-major)
+                    const uint64_t ad = kk * a_step, bd = kk * b_step;
                     const uint32_t acc0 = (i > 0 || kk > 0) ? 1u : 0u;
                     if (STRICT) {
                         // small terms first, then the leading term
-                        umma_tf32(tmem_base, a_lo + adv, b_hi + adv, idesc, acc0);
-                        umma_tf32(tmem_base, a_hi + adv, b_lo + adv, idesc, 1u);
-                        umma_tf32(tmem_base, a_hi + adv, b_hi + adv, idesc, 1u);
+                        umma_tf32(tmem_base, a_lo + ad, b_hi + bd, idesc, acc0);
+                        umma_tf32(tmem_base, a_hi + ad, b_lo + bd, idesc, 1u);
+                        umma_tf32(tmem_base, a_hi + ad, b_hi + bd, idesc, 1u);
                     } else {
-                        umma_tf32(tmem_base, a_hi + adv, b_hi + adv, idesc, acc0);
+                        umma_tf32(tmem_base, a_hi + ad, b_hi + bd, idesc, acc0);
                     }
                 }
                 umma_commit(&empty[s]);                                   // frees the stage once these MMAs have read it
@@ -255,8 +283,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tf32_tcgen05_kernel(const 
 }
 
 // ------------------------------------------------------------------------------------------------ operand preparation
-// One fused, bandwidth-bound pass per operand: bring it into K-major [rows][ld] form (transposing if needed) and, in strict
-// mode, split it into hi = tf32_rna(x) (low 13 mantissa bits zero) and lo = x - hi (exact in fp32).
+// One elementwise, bandwidth-bound pass per operand: re-pitch the row-major matrix to 16-byte aligned rows and, in strict
+// mode, split it into hi = tf32_rna(x) (low 13 mantissa bits zero) and lo = x - hi (exact in fp32).  Optionally the rows
+// and/or columns are re-blocked: source blocks of `bw` rows (columns) land at multiples of `bwp` >= bw in the destination,
+// the padding is zero.  The LSTM layer uses this to start every (gate, direction) block of H cells on a 16-byte boundary,
+// which TMA needs for sub-views along the contiguous dimension.
 __device__ __forceinline__ void split_tf32(float v, float &hi, float &lo)
 {
     uint32_t h;
@@ -265,47 +296,35 @@ __device__ __forceinline__ void split_tf32(float v, float &hi, float &lo)
     lo = __fsub_rn(v, hi);
 }
 
-// src [rows][K] (lds) -> hi/lo [rows][ldd]; grid (rows, ceil(ldd/512)), 128 threads x 4 consecutive k
+// grid (dst_rows, ceil(ldd/512)), 128 threads x 4 consecutive destination columns
 template <bool STRICT>
-__global__ void prep_rows_kernel(int K, const float *__restrict__ src, size_t lds, float *__restrict__ hi, float *__restrict__ lo, size_t ldd)
+__global__ void prep_rows_kernel(int cols, const float *__restrict__ src, size_t lds, float *__restrict__ hi, float *__restrict__ lo, size_t ldd,
+                                 int rbw, int rbwp, int cbw, int cbwp, int dst_cols)
 {
-    const size_t r = blockIdx.x;
-    const int k = (blockIdx.y * blockDim.x + threadIdx.x) * 4;
-    if ((size_t)k >= ldd) return;
-    const float *s = src + r * lds + k;
+    const int rd = blockIdx.x;
+    const int c = (blockIdx.y * blockDim.x + threadIdx.x) * 4;
+    if ((size_t)c >= ldd) return;
+    int rs = rd; bool row_ok = true;
+    if (rbw) { const int b = rd / rbwp, j = rd - b * rbwp; row_ok = j < rbw; rs = b * rbw + j; }
     float v[4], h[4], l[4];
-    const bool vec = ((lds & 3) == 0) && ((reinterpret_cast<uintptr_t>(src) & 15) == 0) && (k + 4 <= K);
-    if (vec) { const float4 q = *reinterpret_cast<const float4 *>(s); v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w; }
-    else {
+    const float *s = src + (size_t)rs * lds;
+    if (!row_ok) {
 #pragma unroll
-        for (int i = 0; i < 4; ++i) v[i] = (k + i < K) ? s[i] : 0.0f;
+        for (int i = 0; i < 4; ++i) v[i] = 0.0f;
+    } else if (!cbw && ((lds & 3) == 0) && ((reinterpret_cast<uintptr_t>(src) & 15) == 0) && (c + 4 <= cols)) {
+        const float4 q = *reinterpret_cast<const float4 *>(s + c); v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w;
+    } else {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            int cs = c + i; bool ok = cs < dst_cols;
+            if (cbw) { const int b = cs / cbwp, j = cs - b * cbwp; ok = ok && j < cbw; cs = b * cbw + j; }
+            v[i] = (ok && cs < cols) ? s[cs] : 0.0f;
+        }
     }
 #pragma unroll
     for (int i = 0; i < 4; ++i) { if (STRICT) split_tf32(v[i], h[i], l[i]); else { h[i] = v[i]; l[i] = 0.0f; } }
-    *reinterpret_cast<float4 *>(hi + r * ldd + k) = make_float4(h[0], h[1], h[2], h[3]);
-    if (STRICT) *reinterpret_cast<float4 *>(lo + r * ldd + k) = make_float4(l[0], l[1], l[2], l[3]);
-}
-
-// src [K][rows] (lds) -> hi/lo [rows][ldd]: 32x32 tiles through shared memory, both sides coalesced
-template <bool STRICT>
-__global__ void prep_transpose_kernel(int K, int rows, const float *__restrict__ src, size_t lds, float *__restrict__ hi,
-                                      float *__restrict__ lo, size_t ldd)
-{
-    __shared__ float t[32][33];
-    const int r0 = blockIdx.x * 32, k0 = blockIdx.y * 32;
-    for (int i = threadIdx.y; i < 32; i += 8) {
-        const int k = k0 + i, r = r0 + threadIdx.x;
-        t[i][threadIdx.x] = (k < K && r < rows) ? src[(size_t)k * lds + r] : 0.0f;
-    }
-    __syncthreads();
-    for (int i = threadIdx.y; i < 32; i += 8) {
-        const int r = r0 + i, k = k0 + threadIdx.x;
-        if (r < rows && k < K) {
-            const float v = t[threadIdx.x][i];
-            if (STRICT) { float h, l; split_tf32(v, h, l); hi[(size_t)r * ldd + k] = h; lo[(size_t)r * ldd + k] = l; }
-            else hi[(size_t)r * ldd + k] = v;
-        }
-    }
+    *reinterpret_cast<float4 *>(hi + (size_t)rd * ldd + c) = make_float4(h[0], h[1], h[2], h[3]);
+    if (STRICT) *reinterpret_cast<float4 *>(lo + (size_t)rd * ldd + c) = make_float4(l[0], l[1], l[2], l[3]);
 }
 
 __global__ void sum_slices_kernel(int M, int N, int nsplit, int batches, const float *__restrict__ partial, int ldp,
@@ -342,19 +361,21 @@ static EncodeTiledFn encode_fn(bl_ctx *ctx)
     return fn;
 }
 
-// K-major operand [rows][K] with leading dimension ld (floats): box = 32 floats (128 B, one swizzle span) x box_rows
-static int make_map(bl_ctx *ctx, CUtensorMap *map, const float *base, int rows, int K, size_t ld, int box_rows)
+// 2D map over a row-major fp32 matrix: `inner` contiguous floats per row, `outer` rows of pitch ld; box = 32 floats (128 B, one
+// swizzle span) x box_outer rows; K-major views use the 16-byte-chunk 128B swizzle, MN-major views the 32-byte-chunk one.
+// Boxes running past either extent are zero-filled.
+static int make_map(bl_ctx *ctx, CUtensorMap *map, const float *base, int inner, int outer, size_t ld, int box_outer, bool mn_major)
 {
     EncodeTiledFn fn = encode_fn(ctx);
     if (!fn) return 1;
-    const cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
+    const cuuint64_t dims[2] = {(cuuint64_t)inner, (cuuint64_t)outer};
     const cuuint64_t strides[1] = {(cuuint64_t)ld * sizeof(float)};
-    const cuuint32_t box[2] = {(cuuint32_t)TC_BK, (cuuint32_t)box_rows};
+    const cuuint32_t box[2] = {(cuuint32_t)TC_BK, (cuuint32_t)box_outer};
     const cuuint32_t estr[2] = {1, 1};
     const CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float *>(base), dims, strides, box, estr,
-                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, mn_major ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) return fail(ctx, "cuTensorMapEncodeTiled failed (%d) rows=%d K=%d ld=%zu", (int)r, rows, K, ld);
+    if (r != CUDA_SUCCESS) return fail(ctx, "cuTensorMapEncodeTiled failed (%d) inner=%d outer=%d ld=%zu", (int)r, inner, outer, ld);
     return 0;
 }
 
@@ -370,49 +391,62 @@ static int launch_tc(bl_ctx *ctx, const GemmTcParams &p, dim3 grid)
     return 0;
 }
 
-size_t tc_operand_ld(int K) { return ((size_t)K + 3) & ~(size_t)3; }
+size_t tc_operand_ld(int cols) { return ((size_t)cols + 3) & ~(size_t)3; }
 
-// Fills `out` with a K-major view of src ([rows][K] if kmajor else [K][rows], leading dimension ld_src).  hi/lo are caller-owned
-// buffers of rows*tc_operand_ld(K) floats (lo unused in fast mode).  In fast mode an already aligned K-major source is used in place.
-int tc_prepare(bl_ctx *ctx, const float *src, int rows, int K, size_t ld_src, bool kmajor, bool strict, float *hi, float *lo, TcOperand *out)
+static int reblocked(int n, int bw, int bwp) { return bw ? (n / bw) * bwp : n; }
+
+size_t tc_operand_elems(int rows, int cols, int rbw, int rbwp, int cbw, int cbwp)
+{
+    return (size_t)reblocked(rows, rbw, rbwp) * tc_operand_ld(reblocked(cols, cbw, cbwp));
+}
+
+// Fills `out` with the prepared form of the row-major matrix src[rows][cols] (leading dimension ld_src).  hi/lo are caller-owned
+// buffers of tc_operand_elems() floats (lo unused in fast mode).  In fast mode an already aligned source without re-blocking is
+// used in place.
+int tc_prepare(bl_ctx *ctx, const float *src, int rows, int cols, size_t ld_src, bool strict, float *hi, float *lo, TcOperand *out,
+               int rbw, int rbwp, int cbw, int cbwp)
 {
     TimedRegion timed(ctx, 0);
-    out->rows = rows; out->K = K; out->strict = strict;
-    const bool aligned = kmajor && ((ld_src & 3) == 0) && ((reinterpret_cast<uintptr_t>(src) & 15) == 0);
-    if (!strict && aligned) { out->hi = src; out->lo = nullptr; out->ld = ld_src; return 0; }
-    const size_t ldd = tc_operand_ld(K);
-    if (kmajor) {
-        dim3 grid(rows, cdiv((int)ldd, 512));
-        if (strict) prep_rows_kernel<true><<<grid, 128, 0, ctx->stream>>>(K, src, ld_src, hi, lo, ldd);
-        else        prep_rows_kernel<false><<<grid, 128, 0, ctx->stream>>>(K, src, ld_src, hi, lo, ldd);
-    } else {
-        dim3 grid(cdiv(rows, 32), cdiv(K, 32));
-        if (grid.y > 65535) return fail(ctx, "tc_prepare: K too large for the transpose grid");
-        if (strict) prep_transpose_kernel<true><<<grid, dim3(32, 8), 0, ctx->stream>>>(K, rows, src, ld_src, hi, lo, ldd);
-        else        prep_transpose_kernel<false><<<grid, dim3(32, 8), 0, ctx->stream>>>(K, rows, src, ld_src, hi, lo, ldd);
-    }
+    if ((rbw && (rows % rbw || rbwp < rbw)) || (cbw && (cols % cbw || cbwp < cbw))) return fail(ctx, "tc_prepare: bad re-blocking");
+    const int drows = reblocked(rows, rbw, rbwp), dcols = reblocked(cols, cbw, cbwp);
+    out->rows = drows; out->cols = dcols; out->strict = strict;
+    const bool aligned = ((ld_src & 3) == 0) && ((reinterpret_cast<uintptr_t>(src) & 15) == 0);
+    if (!strict && aligned && !rbw && !cbw) { out->hi = src; out->lo = nullptr; out->ld = ld_src; return 0; }
+    const size_t ldd = tc_operand_ld(dcols);
+    dim3 grid(drows, cdiv((int)ldd, 512));
+    if (strict) prep_rows_kernel<true><<<grid, 128, 0, ctx->stream>>>(cols, src, ld_src, hi, lo, ldd, rbw, rbwp, cbw, cbwp, dcols);
+    else        prep_rows_kernel<false><<<grid, 128, 0, ctx->stream>>>(cols, src, ld_src, hi, lo, ldd, rbw, rbwp, cbw, cbwp, dcols);
     BL_LAUNCHED(ctx);
     out->hi = hi; out->lo = strict ? lo : nullptr; out->ld = ldd;
     return 0;
 }
 
-// C[M x N] row-major (ldc) (+)= A[a_row0 .. +M][a_k0 .. +K] * B[b_row0 .. +N][b_k0 .. +K]^T on prepared operands
-int tc_gemm(bl_ctx *ctx, int M, int N, int K, const TcOperand &A, int a_row0, int a_k0, const TcOperand &B, int b_row0, int b_k0,
-            float *C, int ldc, int accumulate)
+// C[M x N] row-major (ldc) (+)= A * B^T with A = M x K and B = N x K views of prepared operands
+int tc_gemm(bl_ctx *ctx, int M, int N, int K, const TcView &A, const TcView &B, float *C, int ldc, int accumulate)
 {
-    return tc_gemm_batched(ctx, M, N, K, A, a_row0, a_k0, B, b_row0, b_k0, C, ldc, accumulate, 1, 0, 0);
+    return tc_gemm_batched(ctx, M, N, K, A, B, C, ldc, accumulate, 1, 0, 0);
 }
 
-// `batches` products sharing B: batch b uses A rows [a_row0 + b*a_batch_rows, +M) and writes C + b*c_batch_stride
-int tc_gemm_batched(bl_ctx *ctx, int M, int N, int K, const TcOperand &A, int a_row0, int a_k0, const TcOperand &B, int b_row0, int b_k0,
-                    float *C, int ldc, int accumulate, int batches, int a_batch_rows, long long c_batch_stride)
+static int view_check(bl_ctx *ctx, const TcView &v, int mn_extent, int K, const char *which)
+{
+    const int MN = v.mn_major ? v.op->cols : v.op->rows, KK = v.mn_major ? v.op->rows : v.op->cols;
+    if (v.mn0 < 0 || v.k0 < 0 || v.mn0 + mn_extent > MN || v.k0 + K > KK) return fail(ctx, "tc_gemm: %s sub-view out of range", which);
+    // sub-views along the contiguous dimension must start on a 16-byte boundary (TMA global address alignment)
+    if ((v.mn_major ? v.mn0 : v.k0) & 3) return fail(ctx, "tc_gemm: %s sub-view offset along the contiguous dimension must be a multiple of 4 floats", which);
+    return 0;
+}
+
+// `batches` products sharing B: batch b uses the A view shifted by b*a_batch_mn along MN and writes C + b*c_batch_stride
+int tc_gemm_batched(bl_ctx *ctx, int M, int N, int K, const TcView &A, const TcView &B, float *C, int ldc, int accumulate,
+                    int batches, int a_batch_mn, long long c_batch_stride)
 {
     TimedRegion timed(ctx, 0);
-    const bool strict = A.strict;
-    if (A.strict != B.strict) return fail(ctx, "tc_gemm: operands prepared for different precision modes");
-    const int a_rows_total = (batches - 1) * a_batch_rows + M;
-    if (a_row0 + a_rows_total > A.rows || b_row0 + N > B.rows || a_k0 + K > A.K || b_k0 + K > B.K) return fail(ctx, "tc_gemm: sub-view out of range");
-    if ((a_k0 | b_k0) & 3) return fail(ctx, "tc_gemm: K offsets must be multiples of 4 floats (TMA box starts are 16-byte aligned)");
+    const bool strict = A.op->strict;
+    if (A.op->strict != B.op->strict) return fail(ctx, "tc_gemm: operands prepared for different precision modes");
+    const int a_mn_total = (batches - 1) * a_batch_mn + M;
+    BL_CHECK(view_check(ctx, A, a_mn_total, K, "A"));
+    BL_CHECK(view_check(ctx, B, N, K, "B"));
+    if (A.mn_major && (a_batch_mn & 3)) return fail(ctx, "tc_gemm: batch stride of an MN-major A must be a multiple of 4 floats");
     // strict tiles: BLSTM_TC_BN=256 selects 128x256 tiles with a 2-stage ring (less L2 traffic per MMA, half the per-tile overhead)
     static const int bn_strict_env = getenv("BLSTM_TC_BN") ? atoi(getenv("BLSTM_TC_BN")) : 128;
     const int BN_STRICT = (bn_strict_env == 256) ? 256 : 128; constexpr int BN_FAST = 256;
@@ -435,16 +469,20 @@ int tc_gemm_batched(bl_ctx *ctx, int M, int N, int K, const TcOperand &A, int a_
         BL_CHECK(ensure_scratch2(ctx, (size_t)nsplit * batches * M * ldp * sizeof(float) + 64));
         p.partial = reinterpret_cast<float *>((reinterpret_cast<uintptr_t>(ctx->scratch2) + 15) & ~(uintptr_t)15);
     }
-    // the maps cover rows [row0, row0+M) and K extent [0, k0+K): boxes running past either edge are zero-filled
-    BL_CHECK(make_map(ctx, &p.tmA, A.hi + (size_t)a_row0 * A.ld, a_rows_total, a_k0 + K, A.ld, TC_BM));
-    BL_CHECK(make_map(ctx, &p.tmB, B.hi + (size_t)b_row0 * B.ld, N, b_k0 + K, B.ld, BN));
-    if (strict) {
-        BL_CHECK(make_map(ctx, &p.tmAlo, A.lo + (size_t)a_row0 * A.ld, a_rows_total, a_k0 + K, A.ld, TC_BM));
-        BL_CHECK(make_map(ctx, &p.tmBlo, B.lo + (size_t)b_row0 * B.ld, N, b_k0 + K, B.ld, BN));
-    } else { p.tmAlo = p.tmA; p.tmBlo = p.tmB; }
-    p.C = C; p.ldc = ldc; p.M = M; p.N = N; p.K = K; p.a_k0 = a_k0; p.b_k0 = b_k0;
+    // the maps cover exactly the sub-view: boxes running past its MN or K extent are zero-filled
+    auto maps = [&](const TcView &v, int mn_extent, int box_mn, CUtensorMap *hi, CUtensorMap *lo) -> int {
+        const size_t off = v.mn_major ? (size_t)v.k0 * v.op->ld + v.mn0 : (size_t)v.mn0 * v.op->ld + v.k0;
+        const int inner = v.mn_major ? mn_extent : K, outer = v.mn_major ? K : mn_extent, box_outer = v.mn_major ? TC_BK : box_mn;
+        BL_CHECK(make_map(ctx, hi, v.op->hi + off, inner, outer, v.op->ld, box_outer, v.mn_major));
+        if (strict) BL_CHECK(make_map(ctx, lo, v.op->lo + off, inner, outer, v.op->ld, box_outer, v.mn_major));
+        else *lo = *hi;
+        return 0;
+    };
+    BL_CHECK(maps(A, a_mn_total, TC_BM, &p.tmA, &p.tmAlo));
+    BL_CHECK(maps(B, N, BN, &p.tmB, &p.tmBlo));
+    p.C = C; p.ldc = ldc; p.M = M; p.N = N; p.K = K; p.a_mn = A.mn_major ? 1 : 0; p.b_mn = B.mn_major ? 1 : 0;
     p.kblocks_per_split = kbs; p.accumulate = accumulate; p.ldp = (int)ldp;
-    p.batches = batches; p.mt_per_batch = cdiv(M, TC_BM); p.a_batch_rows = a_batch_rows; p.c_batch_stride = c_batch_stride;
+    p.batches = batches; p.mt_per_batch = cdiv(M, TC_BM); p.a_batch_rows = a_batch_mn; p.c_batch_stride = c_batch_stride;
     dim3 grid(cdiv(N, BN), batches * cdiv(M, TC_BM), nsplit);
     if (grid.y > 65535) return fail(ctx, "tc_gemm: M too large");
     if (strict && BN_STRICT == 256) BL_CHECK((launch_tc<256, true, 2>(ctx, p, grid)));
@@ -464,14 +502,14 @@ int gemm_tf32_tc(bl_ctx *ctx, int M, int N, int K, const float *A, size_t lda, b
                  float *C, int ldc, int accumulate, int mode)
 {
     const bool strict = (mode == BL_GEMM_STRICT);
-    const size_t ldk = tc_operand_ld(K);
-    const size_t a_elems = (size_t)M * ldk, b_elems = (size_t)N * ldk;
+    const int ar = a_kmajor ? M : K, ac = a_kmajor ? K : M, br = b_kmajor ? N : K, bc = b_kmajor ? K : N;
+    const size_t a_elems = tc_operand_elems(ar, ac), b_elems = tc_operand_elems(br, bc);
     BL_CHECK(ensure_scratch(ctx, 2 * (a_elems + b_elems) * sizeof(float) + 64));
     float *S = reinterpret_cast<float *>((reinterpret_cast<uintptr_t>(ctx->scratch) + 15) & ~(uintptr_t)15);
     TcOperand a, b;
-    BL_CHECK(tc_prepare(ctx, A, M, K, lda, a_kmajor, strict, S, S + a_elems, &a));
-    BL_CHECK(tc_prepare(ctx, B, N, K, ldb, b_kmajor, strict, S + 2 * a_elems, S + 2 * a_elems + b_elems, &b));
-    return tc_gemm(ctx, M, N, K, a, 0, 0, b, 0, 0, C, ldc, accumulate);
+    BL_CHECK(tc_prepare(ctx, A, ar, ac, lda, strict, S, S + a_elems, &a));
+    BL_CHECK(tc_prepare(ctx, B, br, bc, ldb, strict, S + 2 * a_elems, S + 2 * a_elems + b_elems, &b));
+    return tc_gemm(ctx, M, N, K, TcView{&a, !a_kmajor, 0, 0}, TcView{&b, !b_kmajor, 0, 0}, C, ldc, accumulate);
 }
 
 } // namespace bl

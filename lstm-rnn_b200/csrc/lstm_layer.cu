@@ -13,6 +13,7 @@
 // and the output errors dY [N][L] are read directly (no ResortOutputErrorsFn pass, :163-188).
 #include "lstm_recurrent.cuh"
 #include "gemm_tc.cuh"
+#include <cstdint>
 #include <cstdlib>
 
 namespace bl {
@@ -28,8 +29,12 @@ struct bl_lstm_plan {
     bool reg_f, reg_b;       // register-resident persistent kernels (lstm_recurrent_reg.cu) vs shared-memory ones
     float *acts, *deltas, *cst, *cerr, *hx, *dx, *gpart;
     long long *trace;
-    float *tcbuf;            // prepared tensor-core operands of the backward pass (hi/lo of deltas, deltas^T, X^T, Y^T, Win^T)
+    float *tcbuf;            // prepared tensor-core operands (hi then lo of each): X, Win (forward); deltas, Y, Win re-blocked (backward)
     size_t tcbuf_elems;
+    float *tc_X, *tc_Wf, *tc_D, *tc_Y, *tc_Wb;
+    size_t tc_eX, tc_eWf, tc_eD, tc_eY, tc_eWb;
+    bl::TcOperand xsplit;    // strict split of the forward pass's X, reused by the backward pass of the same fraction
+    const float *xsplit_src; int xsplit_ld, xsplit_T;
     unsigned *flags_f, *flags_b;
     int gsplit;
     int lastT;
@@ -117,6 +122,7 @@ int bl_lstm_plan_create(bl_ctx *ctx, int P, int L, int bidirectional, int S, int
     pl->flags_f = pl->flags_b = nullptr;
     pl->trace = nullptr;
     pl->tcbuf = nullptr; pl->tcbuf_elems = 0;
+    pl->xsplit_src = nullptr; pl->xsplit_ld = 0; pl->xsplit_T = 0;
 
     const int cap = ctx->smem_optin - 2048;      // room for the kernels' static shared memory (exp table) and the driver's reserve
     // tuning overrides (tools/sweep_geometry.py): sequence groups / sub-CTAs / threads of either kernel, and the kernel family
@@ -177,6 +183,31 @@ int bl_lstm_plan_info(const bl_lstm_plan *pl, int *o)
     return 0;
 }
 
+// lazily allocates the plan's prepared-operand buffers (only layers large enough for the tensor-core path need them)
+static int plan_tc_buffers(bl_lstm_plan *pl)
+{
+    if (pl->tcbuf) return 0;
+    bl_ctx *ctx = pl->ctx;
+    const int P = pl->P, L = pl->L, H = pl->H, Hp = (H + 3) & ~3, nb = 4 * pl->ndir;
+    const int maxN = pl->maxT * pl->S;
+    pl->tc_eX = bl::tc_operand_elems(maxN, P);
+    pl->tc_eWf = bl::tc_operand_elems(4 * L, P);
+    pl->tc_eD = bl::tc_operand_elems(maxN, 4 * L, 0, 0, H, Hp);
+    pl->tc_eY = bl::tc_operand_elems(maxN, L, 0, 0, H, Hp);
+    pl->tc_eWb = bl::tc_operand_elems(4 * L, P, H, Hp, 0, 0);
+    (void)nb;
+    const size_t need = 2 * (pl->tc_eX + pl->tc_eWf + pl->tc_eD + pl->tc_eY + pl->tc_eWb) + 16;
+    BL_CUDA(ctx, cudaMalloc(&pl->tcbuf, need * sizeof(float)));
+    pl->tcbuf_elems = need;
+    float *b = reinterpret_cast<float *>((reinterpret_cast<uintptr_t>(pl->tcbuf) + 15) & ~(uintptr_t)15);
+    pl->tc_X = b; b += 2 * pl->tc_eX;
+    pl->tc_Wf = b; b += 2 * pl->tc_eWf;
+    pl->tc_D = b; b += 2 * pl->tc_eD;
+    pl->tc_Y = b; b += 2 * pl->tc_eY;
+    pl->tc_Wb = b;
+    return 0;
+}
+
 int bl_lstm_forward(bl_lstm_plan *pl, const float *W, const float *X, int ldx, const char *patTypes,
                     int T, int Tmin, float *Y, int ldy)
 {
@@ -186,7 +217,19 @@ int bl_lstm_forward(bl_lstm_plan *pl, const float *W, const float *X, int ldx, c
     const int P = pl->P, L = pl->L, H = pl->H, S = pl->S, N = T * S;
     // (1) input projection of all timesteps, all 4 gates, both directions: acts[4L x N] = Win^T[4L x P] * X[P x N]
     //     (the 8 assignProduct calls of LstmLayer.cu:774-784 as one GEMM; Win is the weight vector's first 4LP floats)
-    BL_CHECK(bl_gemm_f32(ctx, 1, 0, 4 * L, N, P, W, P, X, ldx, pl->acts, 4 * L, 0, ctx->gemm_mode));
+    pl->xsplit_src = nullptr;
+    if (bl::tc_wanted(ctx, 4 * L, N, P)) {
+        // acts[N][4L] = X[N][P] * Win[4L][P]^T, both operands K-major; the strict split of X stays in the plan for the backward pass
+        const bool strict = (ctx->gemm_mode == BL_GEMM_STRICT);
+        BL_CHECK(plan_tc_buffers(pl));
+        bl::TcOperand Xs, Ws;
+        BL_CHECK(bl::tc_prepare(ctx, X, N, P, ldx, strict, pl->tc_X, pl->tc_X + pl->tc_eX, &Xs));
+        BL_CHECK(bl::tc_prepare(ctx, W, 4 * L, P, P, strict, pl->tc_Wf, pl->tc_Wf + pl->tc_eWf, &Ws));
+        BL_CHECK(bl::tc_gemm(ctx, N, 4 * L, P, bl::TcView{&Xs, false, 0, 0}, bl::TcView{&Ws, false, 0, 0}, pl->acts, 4 * L, 0));
+        if (strict) { pl->xsplit = Xs; pl->xsplit_src = X; pl->xsplit_ld = ldx; pl->xsplit_T = T; }
+    } else {
+        BL_CHECK(bl_gemm_f32(ctx, 1, 0, 4 * L, N, P, W, P, X, ldx, pl->acts, 4 * L, 0, ctx->gemm_mode));
+    }
     // (2) recurrent sweep, both directions concurrently
     bl::RecFwdParams p;
     p.Wb = W + (size_t)4 * L * P; p.Wi = p.Wb + 4 * L; p.Wp = p.Wi + (size_t)4 * L * H;
@@ -218,57 +261,39 @@ int bl_lstm_backward(bl_lstm_plan *pl, const float *W, const float *X, int ldx, 
     BL_CHECK(pl->reg_b ? bl::launch_lstm_bwd_reg(ctx, p) : bl::launch_lstm_bwd(ctx, p));
 
     if (bl::tc_wanted(ctx, P, 4 * L, N)) {
-        // ---- tensor-core path: every operand is brought into K-major hi/lo form ONCE per layer and reused:
-        //   D  = deltas   [N][4L]      (K = 4L)  -> input error
-        //   DT = deltas^T [4L][N]      (K = N)   -> input-weight gradient and all 8 recurrent-weight gradient blocks (row sub-views)
-        //   XT = X^T      [P][N], YT = Y^T [L][N] (K = N), WT = Win^T [P][4L] (K = 4L)
+        // ---- tensor-core path: every operand is split (hi/lo TF32) ONCE per layer, in its own row-major layout, and read
+        // either K-major or MN-major by the GEMMs -- nothing is transposed in memory.  The (gate, direction) blocks of H
+        // cells are re-pitched to Hp = roundup(H, 4) so that block sub-views start on 16-byte boundaries:
+        //   D' = deltas [N][4*ndir*Hp]     K-major  -> input error;   MN-major -> input- and recurrent-weight gradients
+        //   X' = X      [N][P]             MN-major -> input-weight gradient (the forward pass's split is reused)
+        //   Y' = Y      [N][ndir*Hp]       MN-major -> recurrent-weight gradients (time shift = row offset of the view)
+        //   W' = Win    [4*ndir*Hp][P]     MN-major -> input error
         const bool strict = true;            // gradients always use the strict (3xTF32) mode
-        const size_t ldN = bl::tc_operand_ld(N), ld4L = bl::tc_operand_ld(4 * L);
-        const size_t maxN = (size_t)pl->maxT * S, ldNmax = bl::tc_operand_ld((int)maxN);
-        const size_t eD = maxN * ld4L, eDT = (size_t)4 * L * ldNmax, eXT = (size_t)P * ldNmax, eYT = (size_t)L * ldNmax, eWT = (size_t)P * ld4L;
-        const size_t need = 2 * (eD + eDT + eXT + eYT + eWT) + 16;
-        if (pl->tcbuf_elems < need) {
-            if (pl->tcbuf) { BL_CUDA(ctx, cudaStreamSynchronize(ctx->stream)); BL_CUDA(ctx, cudaFree(pl->tcbuf)); pl->tcbuf = nullptr; }
-            BL_CUDA(ctx, cudaMalloc(&pl->tcbuf, need * sizeof(float)));
-            pl->tcbuf_elems = need;
-        }
-        float *b = pl->tcbuf;
-        float *Dh = b, *Dl = Dh + eD, *DTh = Dl + eD, *DTl = DTh + eDT, *XTh = DTl + eDT, *XTl = XTh + eXT,
-              *YTh = XTl + eXT, *YTl = YTh + eYT, *WTh = YTl + eYT, *WTl = WTh + eWT;
-        bl::TcOperand D, DT, XT, YT, WT;
-        BL_CHECK(bl::tc_prepare(ctx, pl->deltas, 4 * L, N, 4 * L, /*kmajor=*/false, strict, DTh, DTl, &DT));
-        BL_CHECK(bl::tc_prepare(ctx, X, P, N, ldx, false, strict, XTh, XTl, &XT));
-        BL_CHECK(bl::tc_prepare(ctx, Y, L, N, ldy, false, strict, YTh, YTl, &YT));
-        (void)ldN;
-        // (2) error to the preceding layer: dX[N][P] = deltas[N][4L] * Win^T[P][4L]^T   (the 8 products of :996-1006)
+        const int nb = 4 * pl->ndir, Hp = (H + 3) & ~3;
+        BL_CHECK(plan_tc_buffers(pl));
+        bl::TcOperand D, Xs, Ys, Ws;
+        BL_CHECK(bl::tc_prepare(ctx, pl->deltas, N, 4 * L, 4 * L, strict, pl->tc_D, pl->tc_D + pl->tc_eD, &D, 0, 0, H, Hp));
+        if (pl->xsplit_src == X && pl->xsplit_ld == ldx && pl->xsplit_T == T) Xs = pl->xsplit;
+        else BL_CHECK(bl::tc_prepare(ctx, X, N, P, ldx, strict, pl->tc_X, pl->tc_X + pl->tc_eX, &Xs));
+        BL_CHECK(bl::tc_prepare(ctx, Y, N, L, ldy, strict, pl->tc_Y, pl->tc_Y + pl->tc_eY, &Ys, 0, 0, H, Hp));
+        // (2) error to the preceding layer: dX[N][P] = deltas[N][4L] * Win[4L][P]   (the 8 products of :996-1006)
         if (dX) {
-            BL_CHECK(bl::tc_prepare(ctx, pl->deltas, N, 4 * L, 4 * L, true, strict, Dh, Dl, &D));
-            BL_CHECK(bl::tc_prepare(ctx, W, P, 4 * L, P, false, strict, WTh, WTl, &WT));
-            BL_CHECK(bl::tc_gemm(ctx, N, P, 4 * L, D, 0, 0, WT, 0, 0, dX, lddx, 0));
+            BL_CHECK(bl::tc_prepare(ctx, W, 4 * L, P, P, strict, pl->tc_Wb, pl->tc_Wb + pl->tc_eWb, &Ws, H, Hp, 0, 0));
+            BL_CHECK(bl::tc_gemm(ctx, N, P, nb * Hp, bl::TcView{&D, false, 0, 0}, bl::TcView{&Ws, true, 0, 0}, dX, lddx, 0));
         }
-        // (3) input weight gradients: dWin[4L][P] = deltas^T[4L][N] * X^T[P][N]^T   (ComputeWeightUpdateFn case 0x0, :372-389)
-        BL_CHECK(bl::tc_gemm(ctx, 4 * L, P, N, DT, 0, 0, XT, 0, 0, dW, P, 0));
+        // (3) input weight gradients: dWin[4L][P] = deltas^T * X, one [H x P] row block per (gate, direction)
+        //     (ComputeWeightUpdateFn case 0x0, :372-389)
+        BL_CHECK(bl::tc_gemm_batched(ctx, H, P, N, bl::TcView{&D, true, 0, 0}, bl::TcView{&Xs, true, 0, 0}, dW, P, 0,
+                                     /*batches=*/nb, /*a_batch_mn=*/Hp, /*c_batch_stride=*/(long long)H * P));
         // (4) recurrent weight gradients, one [H x H] block per (gate, direction) (case 0x8, :411-437, 493-500):
         //     fw: dW[j][k] = sum_{n>=S} delta[n,j] * h[n-S,k];   bw: dW[j][k] = sum_{n<N-S} delta[n,j] * h[n+S,k]
-        if (N - S > 0 && (S & 3) == 0) {
-            // one launch per direction: the 4 gate blocks are row sub-views of deltas^T (L rows apart) sharing the same shifted Y^T;
-            // the time shift is a K offset of the sub-view (TMA box starts must stay 16-byte aligned: S % 4 == 0)
+        //     one launch per direction: its 4 gate blocks are column sub-views of D' (ndir*Hp apart) sharing the same shifted Y'
+        if (N - S > 0) {
             for (int d = 0; d < pl->ndir; ++d)
-                BL_CHECK(bl::tc_gemm_batched(ctx, H, H, N - S, DT, d * H, d == 0 ? S : 0, YT, d * H, d == 0 ? 0 : S,
-                                             dWint + (size_t)d * H * H, H, 0, /*batches=*/4, /*a_batch_rows=*/L, /*c_batch_stride=*/(long long)L * H));
+                BL_CHECK(bl::tc_gemm_batched(ctx, H, H, N - S, bl::TcView{&D, true, d * Hp, d == 0 ? S : 0}, bl::TcView{&Ys, true, d * Hp, d == 0 ? 0 : S},
+                                             dWint + (size_t)d * H * H, H, 0, /*batches=*/4, /*a_batch_mn=*/pl->ndir * Hp, /*c_batch_stride=*/(long long)L * H));
         } else {
-            for (int g = 0; g < 4; ++g)
-                for (int d = 0; d < pl->ndir; ++d) {
-                    float *blk = dWint + (size_t)g * L * H + (size_t)d * H * H;
-                    if (N - S > 0) {
-                        // unaligned shift: generic entry (re-prepares the shifted operands from their source pointers)
-                        const int col = g * L + d * H;
-                        const float *A = (d == 0) ? Y : Y + (size_t)S * ldy + H;
-                        const float *B = (d == 0) ? pl->deltas + (size_t)S * 4 * L + col : pl->deltas + col;
-                        BL_CHECK(bl_gemm_f32(ctx, 0, 1, H, H, N - S, A, ldy, B, 4 * L, blk, H, 0, BL_GEMM_STRICT));
-                    } else
-                        BL_CHECK(bl_memset(ctx, blk, 0, (size_t)H * H * sizeof(float)));
-                }
+            BL_CHECK(bl_memset(ctx, dWint, 0, (size_t)4 * L * H * sizeof(float)));
         }
     } else {
         // (2) error to the preceding layer: dX[P x N] = Win[P x 4L] * deltas[4L x N]   (the 8 products of :996-1006)

@@ -297,6 +297,12 @@ def test_network_parity_with_tensor_core_gemms(oracle, gpu_ctx):
         gpu_ctx.set_gemm_mode(1)
         worst = check_net(oracle, gpu_ctx, net_json, 16, lengths, 33, 0, seed=9, tol=2e-3)
         print("fast tcgen05 worst rel err %.2e" % worst)
+        gpu_ctx.set_gemm_mode(0)
+        # cells per direction not a multiple of 4 (blocks re-pitched to 16-byte boundaries), unidirectional layer, odd number
+        # of parallel sequences (the time shift of the recurrent-weight gradient is a row offset of an MN-major view)
+        odd = synth.network_json(37, [126, ("lstm", 50), 250], 21)
+        worst = check_net(oracle, gpu_ctx, odd, 5, [3, 8, 11, 11, 14], 21, 0, seed=4)
+        print("strict tcgen05, odd sizes: worst rel err %.2e" % worst)
     finally:
         gpu_ctx.set_gemm_mode(0)
         gpu_ctx.set_gemm_backend(0)
