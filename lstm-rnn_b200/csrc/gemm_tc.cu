@@ -282,6 +282,197 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tf32_tcgen05_kernel(const 
     }
 }
 
+// ------------------------------------------------------------------------------------------------ the 2-CTA (cta_group::2) kernel
+// A TF32 MMA of 128 x 128 x 8 reads 8 KB of shared memory in 64 tensor-core cycles = 128 B/clk, the whole shared-memory
+// bandwidth of an SM, and the 3xTF32 scheme reads every operand tile three times: the single-CTA kernel above is bound by
+// shared memory (and by L2 -> SM traffic), not by the tensor pipe.  Here two CTAs of a cluster (two SMs) share one
+// 256 x 256 output tile: each holds its own 128 rows of A and HALF of the B tile (128 of the 256 columns), the leader CTA
+// issues tcgen05.mma.cta_group::2 (M = 256, N = 256) and each SM accumulates its 128 x 256 half in its own TMEM.  Per SM and
+// per MMA that is the same 8 KB of shared-memory reads for twice the math, and half the L2 traffic per flop.
+//   both CTAs   warp 0 TMA producer (own A rows, own half of B; all complete_tx go to the LEADER's full barrier),
+//               warp 2 TMEM alloc/dealloc (cta_group::2), warps 4-7 epilogue of the CTA's own 128 rows
+//   leader      warp 1 issues the MMAs; tcgen05.commit ... multicast::cluster releases the stage in both CTAs
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync_all()
+{
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t map_to_cta(uint32_t smem_addr, uint32_t rank)
+{ uint32_t r; asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_addr), "r"(rank)); return r; }
+
+__device__ __forceinline__ void tma_load_2d_2cta(void *smem_dst, const CUtensorMap *map, uint32_t leader_bar, int c0, int c1)
+{
+    asm volatile("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                 :: "r"(smem_u32(smem_dst)), "l"(map), "r"(leader_bar), "r"(c0), "r"(c1) : "memory");
+}
+
+__device__ __forceinline__ void umma_tf32_2cta(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        :: "r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+
+__device__ __forceinline__ void umma_commit_2cta(uint64_t *bar)       // arrives on the barrier at this offset in BOTH CTAs
+{
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 :: "r"(smem_u32(bar)), "h"((uint16_t)3) : "memory");
+}
+
+template <bool STRICT, int STAGES>
+__global__ void __launch_bounds__(TC_THREADS, 1) gemm_tf32_tcgen05_2cta_kernel(const __grid_constant__ GemmTcParams p)
+{
+    constexpr int BNH = 128, BN2 = 256;                                   // per-CTA half of B, full tile width
+    constexpr int A_BYTES = TC_BM * TC_BK * 4, B_BYTES = BNH * TC_BK * 4;
+    constexpr int STAGE_BYTES = (STRICT ? 2 : 1) * (A_BYTES + B_BYTES);
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint64_t *full = reinterpret_cast<uint64_t *>(smem + STAGES * STAGE_BYTES);
+    uint64_t *empty = full + STAGES;
+    uint64_t *tmem_full = empty + STAGES;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tmem_full + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const int batch = blockIdx.y / p.mt_per_batch;
+    const int n0 = (blockIdx.x >> 1) * BN2;
+    const int m0 = (blockIdx.y - batch * p.mt_per_batch) * 2 * TC_BM + (int)rank * TC_BM;   // this CTA's first row inside the batch's block
+    const int a_row0 = batch * p.a_batch_rows + m0;
+    const int b_row0 = n0 + (int)rank * BNH;
+    const int kb_total = (p.K + TC_BK - 1) / TC_BK;
+    const int kb_begin = blockIdx.z * p.kblocks_per_split;
+    const int kb_end = min(kb_total, kb_begin + p.kblocks_per_split);
+    const int nkb = kb_end - kb_begin;
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" :: "l"(&p.tmA) : "memory");
+        asm volatile("prefetch.tensormap [%0];" :: "l"(&p.tmB) : "memory");
+        if (STRICT) {
+            asm volatile("prefetch.tensormap [%0];" :: "l"(&p.tmAlo) : "memory");
+            asm volatile("prefetch.tensormap [%0];" :: "l"(&p.tmBlo) : "memory");
+        }
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        mbar_init(tmem_full, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(tmem_slot)), "n"(BN2) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    cluster_sync_all();                                                   // the peer's barriers are initialised before anything signals them
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===== TMA producer (both CTAs) =====
+        const int nca = p.a_mn ? TC_BM / 32 : 1, ncb = p.b_mn ? BNH / 32 : 1;
+        const int nload = (STRICT ? 2 : 1) * (nca + ncb);
+        int l = lane;
+        const bool is_lo = l >= nca + ncb; if (is_lo) l -= nca + ncb;
+        const bool is_b = l >= nca; const int chunk = is_b ? l - nca : l;
+        const CUtensorMap *map = is_b ? (is_lo ? &p.tmBlo : &p.tmB) : (is_lo ? &p.tmAlo : &p.tmA);
+        const int mn_major = is_b ? p.b_mn : p.a_mn;
+        const int mn = (is_b ? b_row0 : a_row0) + (mn_major ? chunk * 32 : 0);
+        const int dst_off = (is_lo ? A_BYTES + B_BYTES : 0) + (is_b ? A_BYTES : 0) + (mn_major ? chunk * TC_BK * 128 : 0);
+        for (int i = 0; i < nkb; ++i) {
+            const int s = i % STAGES, round = i / STAGES;
+            if (lane == 0) {
+                mbar_wait(&empty[s], (round & 1) ^ 1);
+                if (rank == 0) mbar_expect_tx(&full[s], 2 * STAGE_BYTES);          // both CTAs' boxes land on the leader's barrier
+            }
+            __syncwarp();
+            if (lane < nload) {
+                const int kc = (kb_begin + i) * TC_BK;
+                uint8_t *dst = smem + s * STAGE_BYTES + dst_off;
+                const uint32_t bar = map_to_cta(smem_u32(&full[s]), 0);
+                if (mn_major) tma_load_2d_2cta(dst, map, bar, mn, kc);
+                else          tma_load_2d_2cta(dst, map, bar, kc, mn);
+            }
+        }
+    } else if (warp == 1 && rank == 0) {
+        // ===== MMA issuer (leader CTA only) =====
+        const uint32_t idesc = make_idesc(2 * TC_BM, BN2, p.a_mn, p.b_mn);
+        const uint64_t a_step = (uint64_t)(((p.a_mn ? 1024 : TC_UMMA_K * 4)) >> 4), b_step = (uint64_t)(((p.b_mn ? 1024 : TC_UMMA_K * 4)) >> 4);
+        for (int i = 0; i < nkb; ++i) {
+            const int s = i % STAGES, round = i / STAGES;
+            mbar_wait(&full[s], round & 1);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            if (elect_one()) {
+                const uint8_t *st = smem + s * STAGE_BYTES;
+                const uint64_t a_hi = make_smem_desc(st, p.a_mn), b_hi = make_smem_desc(st + A_BYTES, p.b_mn);
+                const uint64_t a_lo = make_smem_desc(st + A_BYTES + B_BYTES, p.a_mn), b_lo = make_smem_desc(st + 2 * A_BYTES + B_BYTES, p.b_mn);
+#pragma unroll
+                for (int kk = 0; kk < TC_BK / TC_UMMA_K; ++kk) {
+                    const uint64_t ad = kk * a_step, bd = kk * b_step;
+                    const uint32_t acc0 = (i > 0 || kk > 0) ? 1u : 0u;
+                    if (STRICT) {
+                        umma_tf32_2cta(tmem_base, a_lo + ad, b_hi + bd, idesc, acc0);
+                        umma_tf32_2cta(tmem_base, a_hi + ad, b_lo + bd, idesc, 1u);
+                        umma_tf32_2cta(tmem_base, a_hi + ad, b_hi + bd, idesc, 1u);
+                    } else {
+                        umma_tf32_2cta(tmem_base, a_hi + ad, b_hi + bd, idesc, acc0);
+                    }
+                }
+                umma_commit_2cta(&empty[s]);
+                if (i == nkb - 1) umma_commit_2cta(tmem_full);
+            }
+            __syncwarp();
+        }
+    } else if (warp >= 4) {
+        // ===== epilogue (both CTAs): own 128 rows x 256 columns =====
+        const int ew = warp & 3;
+        const int row = m0 + ew * 32 + lane;
+        if (nkb > 0) {
+            mbar_wait(tmem_full, 0);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        }
+        float *out = p.partial ? p.partial + ((size_t)blockIdx.z * p.batches + batch) * p.M * p.ldp : p.C + (size_t)batch * p.c_batch_stride;
+        const int ldo = p.partial ? p.ldp : p.ldc;
+        const bool acc = (!p.partial) && p.accumulate;
+        const bool vec_ok = ((ldo & 3) == 0) && ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
+#pragma unroll 1
+        for (int c = 0; c < BN2; c += 32) {
+            if (n0 + c >= p.N) break;
+            float v[32];
+            if (nkb > 0) {
+                tmem_ld32(tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)c, v);
+            } else {
+#pragma unroll
+                for (int i = 0; i < 32; ++i) v[i] = 0.0f;
+            }
+            if (row < p.M) {
+                float *dst = out + (size_t)row * ldo + n0 + c;
+                if (vec_ok && n0 + c + 32 <= p.N) {
+#pragma unroll
+                    for (int i = 0; i < 32; i += 4) {
+                        float4 o = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+                        if (acc) { const float4 old = *reinterpret_cast<const float4 *>(dst + i); o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w; }
+                        *reinterpret_cast<float4 *>(dst + i) = o;
+                    }
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i)
+                        if (n0 + c + i < p.N) dst[i] = acc ? dst[i] + v[i] : v[i];
+                }
+            }
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    }
+    __syncthreads();
+    cluster_sync_all();                                                   // neither CTA may free TMEM or exit while the pair is still running
+    if (warp == 2) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" :: "r"(tmem_base), "n"(BN2) : "memory");
+    }
+}
+
 // ------------------------------------------------------------------------------------------------ operand preparation
 // One elementwise, bandwidth-bound pass per operand: re-pitch the row-major matrix to 16-byte aligned rows and, in strict
 // mode, split it into hi = tf32_rna(x) (low 13 mantissa bits zero) and lo = x - hi (exact in fp32).  Optionally the rows
@@ -391,6 +582,24 @@ static int launch_tc(bl_ctx *ctx, const GemmTcParams &p, dim3 grid)
     return 0;
 }
 
+template <bool STRICT, int STAGES>
+static int launch_tc_2cta(bl_ctx *ctx, const GemmTcParams &p, dim3 grid)
+{
+    constexpr int STAGE_BYTES = (STRICT ? 2 : 1) * (TC_BM * TC_BK * 4 + 128 * TC_BK * 4);
+    const int smem = STAGES * STAGE_BYTES + 1024 + 256;
+    auto kernel = gemm_tf32_tcgen05_2cta_kernel<STRICT, STAGES>;
+    BL_CUDA(ctx, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = dim3(TC_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = ctx->stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    BL_CUDA(ctx, cudaLaunchKernelEx(&cfg, kernel, p));
+    BL_LAUNCHED(ctx);
+    return 0;
+}
+
 size_t tc_operand_ld(int cols) { return ((size_t)cols + 3) & ~(size_t)3; }
 
 static int reblocked(int n, int bw, int bwp) { return bw ? (n / bw) * bwp : n; }
@@ -447,11 +656,14 @@ int tc_gemm_batched(bl_ctx *ctx, int M, int N, int K, const TcView &A, const TcV
     BL_CHECK(view_check(ctx, A, a_mn_total, K, "A"));
     BL_CHECK(view_check(ctx, B, N, K, "B"));
     if (A.mn_major && (a_batch_mn & 3)) return fail(ctx, "tc_gemm: batch stride of an MN-major A must be a multiple of 4 floats");
-    // strict tiles: BLSTM_TC_BN=256 selects 128x256 tiles with a 2-stage ring (less L2 traffic per MMA, half the per-tile overhead)
+    // strict mode: 256 x 256 tiles on CTA pairs (cta_group::2) unless BLSTM_TC_2CTA=0; BLSTM_TC_BN=256 selects 128x256 single-CTA tiles
     static const int bn_strict_env = getenv("BLSTM_TC_BN") ? atoi(getenv("BLSTM_TC_BN")) : 128;
+    static const bool pair_env = !(getenv("BLSTM_TC_2CTA") && atoi(getenv("BLSTM_TC_2CTA")) == 0);
+    const bool pair = strict && pair_env;
     const int BN_STRICT = (bn_strict_env == 256) ? 256 : 128; constexpr int BN_FAST = 256;
-    const int BN = strict ? BN_STRICT : BN_FAST;
-    const int tiles = batches * cdiv(M, TC_BM) * cdiv(N, BN);
+    const int BN = pair ? 256 : strict ? BN_STRICT : BN_FAST;
+    const int BMT = pair ? 2 * TC_BM : TC_BM;                              // rows of one output tile
+    const int tiles = batches * cdiv(M, BMT) * cdiv(N, BN) * (pair ? 2 : 1);      // in CTAs
     const int kb_total = cdiv(K, TC_BK);
     int nsplit = 1;
     if (tiles < ctx->num_sms && kb_total >= 16) {
@@ -479,13 +691,14 @@ int tc_gemm_batched(bl_ctx *ctx, int M, int N, int K, const TcView &A, const TcV
         return 0;
     };
     BL_CHECK(maps(A, a_mn_total, TC_BM, &p.tmA, &p.tmAlo));
-    BL_CHECK(maps(B, N, BN, &p.tmB, &p.tmBlo));
+    BL_CHECK(maps(B, N, pair ? 128 : BN, &p.tmB, &p.tmBlo));
     p.C = C; p.ldc = ldc; p.M = M; p.N = N; p.K = K; p.a_mn = A.mn_major ? 1 : 0; p.b_mn = B.mn_major ? 1 : 0;
     p.kblocks_per_split = kbs; p.accumulate = accumulate; p.ldp = (int)ldp;
-    p.batches = batches; p.mt_per_batch = cdiv(M, TC_BM); p.a_batch_rows = a_batch_mn; p.c_batch_stride = c_batch_stride;
-    dim3 grid(cdiv(N, BN), batches * cdiv(M, TC_BM), nsplit);
+    p.batches = batches; p.mt_per_batch = cdiv(M, BMT); p.a_batch_rows = a_batch_mn; p.c_batch_stride = c_batch_stride;
+    dim3 grid(cdiv(N, BN) * (pair ? 2 : 1), batches * cdiv(M, BMT), nsplit);
     if (grid.y > 65535) return fail(ctx, "tc_gemm: M too large");
-    if (strict && BN_STRICT == 256) BL_CHECK((launch_tc<256, true, 2>(ctx, p, grid)));
+    if (pair) BL_CHECK((launch_tc_2cta<true, 3>(ctx, p, grid)));
+    else if (strict && BN_STRICT == 256) BL_CHECK((launch_tc<256, true, 2>(ctx, p, grid)));
     else if (strict) BL_CHECK((launch_tc<128, true, 3>(ctx, p, grid)));
     else        BL_CHECK((launch_tc<BN_FAST, false, 4>(ctx, p, grid)));
     if (nsplit > 1) {
