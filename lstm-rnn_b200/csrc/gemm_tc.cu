@@ -667,7 +667,7 @@ int tc_gemm_batched(bl_ctx *ctx, int M, int N, int K, const TcView &A, const TcV
     const int kb_total = cdiv(K, TC_BK);
     int nsplit = 1;
     if (tiles < ctx->num_sms && kb_total >= 16) {
-        nsplit = cdiv(2 * ctx->num_sms, tiles);
+        nsplit = (2 * ctx->num_sms) / tiles;               // at most two full waves of CTAs: a third, mostly empty wave costs more than it buys
         if (nsplit > kb_total / 8) nsplit = kb_total / 8;
         if (nsplit > 64) nsplit = 64;
         if (nsplit < 1) nsplit = 1;
