@@ -20,6 +20,12 @@ ROOT = os.path.join(os.path.dirname(__file__), "..")
 EXE = os.path.join(ROOT, "lstm-rnn_b200", "currennt_b200")
 
 
+@pytest.fixture(scope="module", autouse=True)
+def _built():
+    if not os.path.exists(EXE):                              # normally built by __graft_entry__.build()
+        subprocess.run(["make", "-C", os.path.join(ROOT, "lstm-rnn_b200"), "currennt_b200"], check=True, capture_output=True)
+
+
 def _with_weights(net_json, weights):
     """network.jsn with a "weights" section (input | bias | internal per layer, TrainableLayer.cu:211-238), full precision."""
     doc = json.loads(net_json) if isinstance(net_json, str) else json.loads(json.dumps(net_json))
