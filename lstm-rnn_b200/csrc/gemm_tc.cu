@@ -26,6 +26,7 @@
 namespace bl {
 
 constexpr int TC_BM = 128, TC_BK = 32, TC_UMMA_K = 8, TC_THREADS = 256;
+constexpr int EPI_LD = 36;                     // row pitch (floats) of the epilogue's 32 x 32 transpose tiles: 16-byte aligned rows, conflict-free float4 access
 
 struct GemmTcParams {
     CUtensorMap tmA, tmAlo, tmB, tmBlo;     // lo maps unused in fast mode
@@ -427,8 +428,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tf32_tcgen05_2cta_kernel(c
         }
     } else if (warp >= 4) {
         // ===== epilogue (both CTAs): own 128 rows x 256 columns =====
+        // tcgen05.ld hands lane r the 32 consecutive columns of row r; storing that directly makes every warp store touch 32
+        // different 128 B lines with 16 B each.  Each warp instead transposes its 32 x 32 block through a private shared
+        // tile so that one store instruction writes 4 complete 128 B lines.
         const int ew = warp & 3;
-        const int row = m0 + ew * 32 + lane;
+        float *stg = reinterpret_cast<float *>(smem + STAGES * STAGE_BYTES + 256) + ew * (32 * EPI_LD);
+        const int row_base = m0 + ew * 32;
         if (nkb > 0) {
             mbar_wait(tmem_full, 0);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -437,6 +442,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tf32_tcgen05_2cta_kernel(c
         const int ldo = p.partial ? p.ldp : p.ldc;
         const bool acc = (!p.partial) && p.accumulate;
         const bool vec_ok = ((ldo & 3) == 0) && ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
+        const int sub_r = lane >> 3, sub_c = (lane & 7) * 4;              // this lane's row (within a group of 4) and first column when storing
 #pragma unroll 1
         for (int c = 0; c < BN2; c += 32) {
             if (n0 + c >= p.N) break;
@@ -447,21 +453,27 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tf32_tcgen05_2cta_kernel(c
 #pragma unroll
                 for (int i = 0; i < 32; ++i) v[i] = 0.0f;
             }
-            if (row < p.M) {
-                float *dst = out + (size_t)row * ldo + n0 + c;
-                if (vec_ok && n0 + c + 32 <= p.N) {
 #pragma unroll
-                    for (int i = 0; i < 32; i += 4) {
-                        float4 o = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
-                        if (acc) { const float4 old = *reinterpret_cast<const float4 *>(dst + i); o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w; }
-                        *reinterpret_cast<float4 *>(dst + i) = o;
-                    }
+            for (int i = 0; i < 32; i += 4) *reinterpret_cast<float4 *>(stg + lane * EPI_LD + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+            __syncwarp();
+            const int col = n0 + c + sub_c;
+#pragma unroll
+            for (int it = 0; it < 8; ++it) {
+                const int r = it * 4 + sub_r, row = row_base + r;
+                if (row >= p.M) continue;
+                float4 o = *reinterpret_cast<const float4 *>(stg + r * EPI_LD + sub_c);
+                float *dst = out + (size_t)row * ldo + col;
+                if (vec_ok && col + 4 <= p.N) {
+                    if (acc) { const float4 old = *reinterpret_cast<const float4 *>(dst); o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w; }
+                    *reinterpret_cast<float4 *>(dst) = o;
                 } else {
+                    const float e[4] = {o.x, o.y, o.z, o.w};
 #pragma unroll
-                    for (int i = 0; i < 32; ++i)
-                        if (n0 + c + i < p.N) dst[i] = acc ? dst[i] + v[i] : v[i];
+                    for (int i = 0; i < 4; ++i)
+                        if (col + i < p.N) dst[i] = acc ? dst[i] + e[i] : e[i];
                 }
             }
+            __syncwarp();
         }
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     }
@@ -586,7 +598,7 @@ template <bool STRICT, int STAGES>
 static int launch_tc_2cta(bl_ctx *ctx, const GemmTcParams &p, dim3 grid)
 {
     constexpr int STAGE_BYTES = (STRICT ? 2 : 1) * (TC_BM * TC_BK * 4 + 128 * TC_BK * 4);
-    const int smem = STAGES * STAGE_BYTES + 1024 + 256;
+    const int smem = STAGES * STAGE_BYTES + 1024 + 256 + 4 * 32 * EPI_LD * 4;       // ring + alignment slack + barriers + epilogue tiles
     auto kernel = gemm_tf32_tcgen05_2cta_kernel<STRICT, STAGES>;
     BL_CUDA(ctx, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     cudaLaunchConfig_t cfg = {};
