@@ -303,7 +303,7 @@ def run_ours(args, rank, world, local_rank):
         if os.path.exists(tpath):        # DRAM bytes per slot and unit of layer size from the committed ncu --set full captures
             tj = json.load(open(tpath))
             traffic = (fwd_b / 40.0 * tj["fwd_dram_bytes_per_slot_per_layer_unit"] + bwd_b / 48.0 * tj["bwd_dram_bytes_per_slot_per_layer_unit"]) / max(n_launch, 1)
-        roofline = {"kernel": "lstm_{fwd,bwd}_persistent_kernel", "bound": "hbm", "achieved": achieved, "peak": pk["hbm_gbs"], "unit": "GB/s",
+        roofline = {"kernel": "lstm_{fwd,bwd}_reg_kernel", "bound": "hbm", "achieved": achieved, "peak": pk["hbm_gbs"], "unit": "GB/s",
                     "frac": achieved / pk["hbm_gbs"], "peak_source": pk["source"], "traffic": traffic,
                     "algorithmic_bytes_per_launch": (fwd_b + bwd_b) / max(n_launch, 1), "avg_launch_ms": rec_ms / max(n_launch, 1),
                     "share_of_kernel_time": share[1] + share[2]}

@@ -1,0 +1,37 @@
+"""Turns the raw output of tools/profile_round.sh (gpurun_out/) into the committed summaries under profiles/.
+Usage: python tools/profile_collect.py r01"""
+import json
+import os
+import shutil
+import subprocess
+import sys
+
+tag = sys.argv[1] if len(sys.argv) > 1 else "r01"
+root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+src, dst = os.path.join(root, "gpurun_out"), os.path.join(root, "profiles")
+
+
+def run(args):
+    return subprocess.run([sys.executable] + args, capture_output=True, text=True, check=True, cwd=root).stdout
+
+
+bench = json.load(open(os.path.join(src, tag + "_bench_1gpu.json")))
+json.dump(bench, open(os.path.join(dst, tag + "_bench_1gpu.json"), "w"), indent=1)
+shutil.copy(os.path.join(src, tag + "_launches.csv"), os.path.join(dst, tag + "_launches.csv"))
+steps = 10          # bench.py --steps 2 --warmup 3 runs (3 + 2) steps in each of its value and e2e passes before the capture limit
+head = ("# ncu --metrics gpu__time_duration.sum --clock-control none -c 3000 python bench.py --steps 2 --warmup 3\n"
+        "# B200, C2 workload, strict mode. Cold-cache serialised times: compare SHARES with bench.py's kernel_classes, not absolutes.\n"
+        "# raw csv: profiles/%s_launches.csv; per-step columns divide by the %d steps captured\n" % (tag, steps))
+open(os.path.join(dst, tag + "_launch_list_summary.txt"), "w").write(head + run(["tools/launch_summary.py", os.path.join(src, tag + "_launches.csv"), str(steps)]))
+for name, what in (("fwd", "lstm_fwd_reg_kernel (largest fraction of the bench, T=780)"), ("bwd", "lstm_bwd_reg_kernel (T=780)"),
+                   ("gemm", "gemm_tf32_tcgen05_2cta_kernel: the GEMM launches of one training step")):
+    rep = os.path.join(src, "%s_%s_full.ncu-rep" % (tag, name))
+    if os.path.exists(rep):
+        text = run(["tools/ncu_summary.py", rep])
+        open(os.path.join(dst, "%s_%s_ncu.txt" % (tag, name)), "w").write(
+            "# ncu --set full --clock-control none --import-source on: %s\n# summary by tools/ncu_summary.py (the .ncu-rep stays in gpurun_out/)\n" % what + text)
+tr = os.path.join(src, tag + "_recurrent_trace.txt")
+if os.path.exists(tr):
+    open(os.path.join(dst, tag + "_recurrent_trace.txt"), "w").write(
+        "# BLSTM_REC_TRACE=1 python tools/trace_recurrent.py 250 100 300 on B200: in-kernel clock64 stamps of lstm_fwd_reg_kernel\n" + open(tr).read())
+print("profiles/ updated:", sorted(f for f in os.listdir(dst) if f.startswith(tag)))

@@ -1,0 +1,23 @@
+#!/bin/bash
+# One GPU call that regenerates the raw material of profiles/ (run under gpurun from the repo root):
+#   gpurun --timeout 1800 -- 'bash tools/profile_round.sh r01'
+# then, back in the container:  python tools/profile_collect.py r01
+set -u
+TAG=${1:-r01}
+OUT=gpurun_out
+mkdir -p $OUT
+# 1. the bench line itself (never taken under a profiler)
+timeout 400 python bench.py 2>$OUT/${TAG}_bench.err | tail -1 > $OUT/${TAG}_bench_1gpu.json
+# 2. launch list of the same command (cold-cache, serialised: compare SHARES)
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 3000 --csv --log-file $OUT/${TAG}_launches.csv \
+    python bench.py --steps 2 --warmup 3 > $OUT/${TAG}_launches.log 2>&1
+# 3. one full capture of each top kernel
+timeout 400 ncu --set full --clock-control none --import-source on -k regex:lstm_fwd_reg -s 4 -c 1 -f -o $OUT/${TAG}_fwd_full \
+    python bench.py --steps 1 --warmup 3 > $OUT/${TAG}_ncu_fwd.log 2>&1
+timeout 400 ncu --set full --clock-control none --import-source on -k regex:lstm_bwd_reg -s 4 -c 1 -f -o $OUT/${TAG}_bwd_full \
+    python bench.py --steps 1 --warmup 3 > $OUT/${TAG}_ncu_bwd.log 2>&1
+timeout 400 ncu --set full --clock-control none --import-source on -k regex:2cta -s 40 -c 13 -f -o $OUT/${TAG}_gemm_full \
+    python bench.py --steps 1 --warmup 3 > $OUT/${TAG}_ncu_gemm.log 2>&1
+# 4. in-kernel phase trace of the forward recurrent kernel (one C2 layer, T=300)
+BLSTM_REC_TRACE=1 timeout 300 python tools/trace_recurrent.py 250 100 300 > $OUT/${TAG}_recurrent_trace.txt 2>&1
+ls -la $OUT | tail -20
