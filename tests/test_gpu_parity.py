@@ -164,6 +164,30 @@ def test_sequence_group_geometries(oracle, gpu_ctx, G, monkeypatch):
     print("G=%d worst rel err %.2e" % (G, worst))
 
 
+@pytest.mark.parametrize("family", ["registers", "smem"])
+def test_both_recurrent_kernel_families(oracle, gpu_ctx, family, monkeypatch):
+    """Register-resident (default) and shared-memory-resident (BLSTM_REC_V=2, the fallback for slices that do not fit the
+    register file) kernels implement the same step protocol and must both hold the parity bar."""
+    import currennt_b200 as cb
+    if family == "smem":
+        monkeypatch.setenv("BLSTM_REC_V", "2")
+    net_json = synth.network_json(13, [48, ("lstm", 27)], 11)
+    info = cb.Net(gpu_ctx, net_json, 6, 16).plan_info(1)
+    assert info["fwd_kernel"] == family and info["bwd_kernel"] == family, info
+    worst = check_net(oracle, gpu_ctx, net_json, 6, [1, 4, 9, 9, 12, 14], 11, 0, seed=21)
+    print(family, "worst rel err %.2e" % worst)
+
+
+def test_extreme_shapes(oracle, gpu_ctx):
+    """parallel_sequences = 1 (the reference's default), single-timestep sequences, one very wide layer."""
+    w = check_net(oracle, gpu_ctx, synth.network_json(7, [18], 5), 1, [9], 5, 0, seed=2)
+    print("S=1 worst rel err %.2e" % w)
+    w = check_net(oracle, gpu_ctx, synth.network_json(7, [18, ("lstm", 6)], 5), 4, [1, 1, 1, 1], 5, 0, seed=3)
+    print("T=1 worst rel err %.2e" % w)
+    w = check_net(oracle, gpu_ctx, synth.network_json(9, [("lstm", 1024)], 4), 2, [3, 4], 4, 0, seed=4)
+    print("H=1024 worst rel err %.2e" % w)
+
+
 def test_repeated_fractions_reuse_buffers(oracle, gpu_ctx):
     """A long fraction followed by a shorter one: stale tails of the previous fraction must not leak (Layer.cpp:134-141)."""
     import currennt_b200 as cb
