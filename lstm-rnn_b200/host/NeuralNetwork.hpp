@@ -33,8 +33,8 @@ public:
     std::vector<std::vector<std::vector<real_t>>> getOutputs();
 
     // data parallelism (no reference counterpart): when a communicator is attached, every trainable
-    // layer's weightUpdates() is all-reduced on the side stream as soon as that layer's backward is enqueued, so the
-    // exchange overlaps the backward of the layers below.  joinGradients() orders the compute stream after them.
+    // layer's weightUpdates() is handed to bl_allreduce_sum_f32 as soon as that layer's backward is enqueued;
+    // joinGradients() completes the reductions (one grouped NCCL call by default, see csrc/comm.cu) before the update.
     void setCommunicator(bl_comm *comm) { m_comm = comm; }
     bl_comm *communicator() const { return m_comm; }
     // a rank whose shard of the fraction is empty still has to take part in the reduction, with zero gradients

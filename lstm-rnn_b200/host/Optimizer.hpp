@@ -18,7 +18,7 @@ public:
     // hybridOnlineBatch == the reference's --hybrid_online_batch / --stochastic: update after every fraction
     SteepestDescentOptimizer(NeuralNetwork &neuralNetwork, real_t learningRate, real_t momentum, bool hybridOnlineBatch = true);
 
-    // one fraction: loadSequences -> forward -> calculateError (+ countCorrect) -> backward (+ overlapped gradient
+    // one fraction: loadSequences -> forward -> calculateError (+ countCorrect) -> backward (+ gradient
     // all-reduce) -> weight update.  The body of the while loop of Optimizer::_processDataSet (Optimizer.cu:46-97).
     StepResult trainFraction(const data_sets::DataSetFraction &frac, bool firstFraction = true);
     // forward + error only (validation / test sets)
