@@ -90,32 +90,44 @@ __device__ __forceinline__ void rg_publish(unsigned *flag)
     }
 }
 
-// previous-step vector (tile, [SGp][RS]) times this thread's 2 x 32 register-resident weights; partials to stage[ks][s][row]
-__device__ __forceinline__ void reg_gemm(const RecGeom &g, const float (&w0)[RG_KC], const float (&w1)[RG_KC],
+// Packed fp32 FMA (Blackwell FFMA2): one instruction performs two IEEE fma.rn -- bit-identical to two fmaf -- and halves the
+// issue slots the step GEMM needs (the FMA datapath rate is unchanged; measured with tools/micro/ffma2.cu).
+__device__ __forceinline__ unsigned long long rg_pack2(float lo, float hi)
+{ unsigned long long r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
+__device__ __forceinline__ void rg_unpack2(unsigned long long v, float &lo, float &hi)
+{ asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ void rg_fma2(unsigned long long &acc, unsigned long long a, unsigned long long b)
+{ asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc) : "l"(a), "l"(b)); }
+
+// previous-step vector (tile, [SGp][RS]) times this thread's 2 x 32 register-resident weights (w[e] = {row rp, row rp+RH} at
+// k = ks*32 + e, packed); partials to stage[ks][s][row]
+__device__ __forceinline__ void reg_gemm(const RecGeom &g, const unsigned long long (&w)[RG_KC],
                                          const float *__restrict__ tile, float *__restrict__ stage, int rp, int ks, int nseq)
 {
     const float *tp = tile + ks * RG_CS;
     float *sp = stage + (ks * g.Spad) * g.RP + rp;
     for (int s0 = 0; s0 < nseq; s0 += 4) {
-        float acc[2][4];
+        unsigned long long acc[4];
 #pragma unroll
-        for (int q = 0; q < 4; ++q) { acc[0][q] = 0.0f; acc[1][q] = 0.0f; }
+        for (int q = 0; q < 4; ++q) acc[q] = 0ull;
         const float *t0 = tp + s0 * g.RS;
 #pragma unroll
         for (int k4 = 0; k4 < RG_KC / 4; ++k4) {
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
                 const float4 h = *reinterpret_cast<const float4 *>(t0 + q * g.RS + k4 * 4);
-                acc[0][q] = fmaf(w0[k4 * 4 + 0], h.x, acc[0][q]); acc[1][q] = fmaf(w1[k4 * 4 + 0], h.x, acc[1][q]);
-                acc[0][q] = fmaf(w0[k4 * 4 + 1], h.y, acc[0][q]); acc[1][q] = fmaf(w1[k4 * 4 + 1], h.y, acc[1][q]);
-                acc[0][q] = fmaf(w0[k4 * 4 + 2], h.z, acc[0][q]); acc[1][q] = fmaf(w1[k4 * 4 + 2], h.z, acc[1][q]);
-                acc[0][q] = fmaf(w0[k4 * 4 + 3], h.w, acc[0][q]); acc[1][q] = fmaf(w1[k4 * 4 + 3], h.w, acc[1][q]);
+                rg_fma2(acc[q], w[k4 * 4 + 0], rg_pack2(h.x, h.x));
+                rg_fma2(acc[q], w[k4 * 4 + 1], rg_pack2(h.y, h.y));
+                rg_fma2(acc[q], w[k4 * 4 + 2], rg_pack2(h.z, h.z));
+                rg_fma2(acc[q], w[k4 * 4 + 3], rg_pack2(h.w, h.w));
             }
         }
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
-            sp[(s0 + q) * g.RP] = acc[0][q];
-            sp[(s0 + q) * g.RP + g.RQt] = acc[1][q];
+            float a0, a1;
+            rg_unpack2(acc[q], a0, a1);
+            sp[(s0 + q) * g.RP] = a0;
+            sp[(s0 + q) * g.RP + g.RQt] = a1;
         }
     }
 }
@@ -156,7 +168,7 @@ __global__ void __launch_bounds__(RG_NT, 1) lstm_fwd_reg_kernel(const RecFwdPara
     const int RH = g.RQt, KSn = g.KS;
     const bool gemm_thread = tid < RH * KSn;
     const int ks = tid / RH, rp = tid - ks * RH;
-    float w0[RG_KC], w1[RG_KC];
+    unsigned long long w[RG_KC];
     {
         const int r0 = rp, r1 = rp + RH;
         const int g0 = r0 / g.CL, c0 = r0 - g0 * g.CL, g1 = r1 / g.CL, c1 = r1 - g1 * g.CL;
@@ -167,8 +179,7 @@ __global__ void __launch_bounds__(RG_NT, 1) lstm_fwd_reg_kernel(const RecFwdPara
 #pragma unroll
         for (int e = 0; e < RG_KC; ++e) {
             const int k = ks * RG_KC + e;
-            w0[e] = (ok0 && k < H) ? __ldg(q0 + k) : 0.0f;
-            w1[e] = (ok1 && k < H) ? __ldg(q1 + k) : 0.0f;
+            w[e] = rg_pack2((ok0 && k < H) ? __ldg(q0 + k) : 0.0f, (ok1 && k < H) ? __ldg(q1 + k) : 0.0f);
         }
     }
 
@@ -223,7 +234,7 @@ __global__ void __launch_bounds__(RG_NT, 1) lstm_fwd_reg_kernel(const RecFwdPara
             for (int i = tid; i < n4; i += RG_NT) dst[i] = __ldcg(src + i);
             __syncthreads();
             if (tr && tid == 0) tr[2] = clock64();
-            if (gemm_thread) reg_gemm(g, w0, w1, tile, stage, rp, ks, nseq);
+            if (gemm_thread) reg_gemm(g, w, tile, stage, rp, ks, nseq);
             __syncthreads();
             if (tr && tid == 0) tr[3] = clock64();
         }
@@ -311,7 +322,7 @@ __global__ void __launch_bounds__(RG_NT, 1) lstm_bwd_reg_kernel(const RecBwdPara
     const int RH = g.RQt, KSn = g.KS;
     const bool gemm_thread = tid < RH * KSn;
     const int ks = tid / RH, rp = tid - ks * RH;
-    float w0[RG_KC], w1[RG_KC];
+    unsigned long long w[RG_KC];
     {
         const int c0 = rp, c1 = rp + RH;
         const bool ok0 = gemm_thread && c0 < ncell, ok1 = gemm_thread && c1 < ncell;
@@ -320,8 +331,7 @@ __global__ void __launch_bounds__(RG_NT, 1) lstm_bwd_reg_kernel(const RecBwdPara
             const int kk = ks * RG_KC + e;
             const int gi = kk / Hp, j = kk - gi * Hp;
             const float *q = p.Wi + (size_t)gi * L * H + (size_t)d * H * H + (size_t)j * H + j0;
-            w0[e] = (ok0 && j < H) ? __ldg(q + c0) : 0.0f;
-            w1[e] = (ok1 && j < H) ? __ldg(q + c1) : 0.0f;
+            w[e] = rg_pack2((ok0 && j < H) ? __ldg(q + c0) : 0.0f, (ok1 && j < H) ? __ldg(q + c1) : 0.0f);
         }
     }
 
@@ -379,7 +389,7 @@ __global__ void __launch_bounds__(RG_NT, 1) lstm_bwd_reg_kernel(const RecBwdPara
             const int n4 = nseq * g.RS / 4;
             for (int i = tid; i < n4; i += RG_NT) dst[i] = __ldcg(src + i);
             __syncthreads();
-            if (gemm_thread) reg_gemm(g, w0, w1, tile, stage, rp, ks, nseq);
+            if (gemm_thread) reg_gemm(g, w, tile, stage, rp, ks, nseq);
             __syncthreads();
         }
 
