@@ -66,6 +66,9 @@ cn_dataset *cn_dataset_create(bl_ctx *ctx, int num_seqs, const int *seq_lengths,
 /* NetCDF-3 classic data files in the reference's schema (data_sets/DataSet.cpp:443-606); `path` may be a comma separated list */
 cn_dataset *cn_dataset_load_netcdf(bl_ctx *ctx, const char *path, int parallel_sequences, float fraction, int truncate_seq,
                                    int training_mode, int rank, int world);
+/* --input_left_context / --input_right_context / --output_time_lag (DataSet.cpp:302-305, 348-393); fractions then carry
+ * input patterns of (left + right + 1) x inputPattSize values */
+int  cn_dataset_set_context(cn_dataset *ds, int left, int right, int output_time_lag);
 void cn_dataset_destroy(cn_dataset *ds);
 /* out6 = {totalSequences, totalTimesteps, minSeqLength, maxSeqLength, numFractions, isClassification} */
 int  cn_dataset_info(const cn_dataset *ds, long *out6);

@@ -122,6 +122,13 @@ void DataSet::setInputNoise(real_t sigma, unsigned seed)
     m_noiseGen.seed(seed + 7919u * (unsigned)m_rank);                             // independent noise per rank
 }
 
+void DataSet::setContext(int left, int right, int outputTimeLag)
+{
+    if (left < 0 || right < 0 || outputTimeLag < 0) throw std::runtime_error("DataSet: negative context / time lag");
+    if (m_pending.valid()) m_pending.wait();
+    m_contextLeft = left; m_contextRight = right; m_outputLag = outputTimeLag;
+}
+
 void DataSet::shuffleSequences()
 {
     std::shuffle(m_sequences.begin(), m_sequences.end(), m_shuffleGen);           // DataSet.cpp:225-229
@@ -157,8 +164,9 @@ int DataSet::numFractions() const
 std::shared_ptr<DataSetFraction> DataSet::makeFraction(int firstSeqIdx)
 {
     const int S = m_parallelSequences, P = m_inputPatternSize, O = m_outputPatternSize;
+    const int ctx = m_contextLeft + m_contextRight + 1, PF = P * ctx;
     std::shared_ptr<DataSetFraction> frac(new DataSetFraction);
-    frac->m_inputPatternSize = P;
+    frac->m_inputPatternSize = PF;
     frac->m_outputPatternSize = O;
     frac->m_parallelSequences = S;
     frac->m_maxSeqLength = std::numeric_limits<int>::min();
@@ -178,32 +186,36 @@ std::shared_ptr<DataSetFraction> DataSet::makeFraction(int firstSeqIdx)
     if (frac->m_seqInfo.empty()) { frac->m_maxSeqLength = 0; frac->m_minSeqLength = 0; return frac; }   // empty shard
 
     const size_t slots = (size_t)frac->m_maxSeqLength * S, maxSlots = (size_t)m_maxSeqLength * S;
-    frac->m_inputs.resize(m_ctx, slots * P, 0, maxSlots * P);
+    frac->m_inputs.resize(m_ctx, slots * PF, 0, maxSlots * PF);
     frac->m_patTypes.resize(m_ctx, slots, PATTYPE_NONE, maxSlots);
     if (m_isClassificationData) frac->m_targetClasses.resize(m_ctx, slots, -1, maxSlots);
     else frac->m_outputs.resize(m_ctx, slots * O, 0, maxSlots * O);
 
+    std::vector<real_t> noisy;
     for (int i = 0; i < S; ++i) {
         if (first + i >= (int)m_sequences.size()) continue;
         const sequence_t &seq = m_sequences[first + i];
+        const real_t *src = m_inputs.data() + seq.inputsBegin * P;
+        if (m_noiseDeviation > 0) {                                               // noise on the sequence, before the splicing (:346-347, 250-266)
+            std::normal_distribution<real_t> dist((real_t)0, m_noiseDeviation);
+            noisy.assign(src, src + (size_t)seq.length * P);
+            for (real_t &x : noisy) x += dist(m_noiseGen);
+            src = noisy.data();
+        }
         for (int t = 0; t < seq.length; ++t) {
             const size_t slot = (size_t)t * S + i;                                // DataSet.cpp:358
-            std::memcpy(frac->m_inputs.data() + slot * P, m_inputs.data() + (seq.inputsBegin + t) * P, sizeof(real_t) * P);
-            if (m_isClassificationData)
-                frac->m_targetClasses[slot] = m_targetClasses[seq.targetsBegin + t];
-            else
-                std::memcpy(frac->m_outputs.data() + slot * O, m_targets.data() + (seq.targetsBegin + t) * O, sizeof(real_t) * O);
-            frac->m_patTypes[slot] = (t == 0) ? PATTYPE_FIRST : (t == seq.length - 1) ? PATTYPE_LAST : PATTYPE_NORMAL;   // :397-406
-        }
-    }
-    if (m_noiseDeviation > 0) {                                                   // DataSet.cpp:250-266, 347
-        std::normal_distribution<real_t> dist((real_t)0, m_noiseDeviation);
-        for (int i = 0; i < S; ++i) {
-            if (first + i >= (int)m_sequences.size()) continue;
-            for (int t = 0; t < m_sequences[first + i].length; ++t) {
-                real_t *x = frac->m_inputs.data() + ((size_t)t * S + i) * P;
-                for (int p = 0; p < P; ++p) x[p] += dist(m_noiseGen);
+            real_t *dst = frac->m_inputs.data() + slot * PF;
+            for (int off = -m_contextLeft; off <= m_contextRight; ++off, dst += P) {   // :348-363 (edges repeat the first / last frame)
+                const int ts = std::min(std::max(t + off, 0), seq.length - 1);
+                std::memcpy(dst, src + (size_t)ts * P, sizeof(real_t) * P);
             }
+            if (m_isClassificationData)                                           // :370-377
+                frac->m_targetClasses[slot] = (t >= m_outputLag) ? m_targetClasses[seq.targetsBegin + t - m_outputLag] : 0;
+            else if (t >= m_outputLag)                                            // :380-393
+                std::memcpy(frac->m_outputs.data() + slot * O, m_targets.data() + (seq.targetsBegin + t - m_outputLag) * O, sizeof(real_t) * O);
+            else
+                for (int o = 0; o < O; ++o) frac->m_outputs[slot * O + o] = 1.0f;
+            frac->m_patTypes[slot] = (t == 0) ? PATTYPE_FIRST : (t == seq.length - 1) ? PATTYPE_LAST : PATTYPE_NORMAL;   // :397-406
         }
     }
     return frac;

@@ -37,6 +37,11 @@ public:
     void setShuffling(bool fractionShuffling, bool sequenceShuffling, unsigned seed);
     // --input_noise_sigma: Gaussian noise added to the inputs of every fraction (DataSet.cpp:250-266)
     void setInputNoise(real_t sigma, unsigned seed);
+    // --input_left_context / --input_right_context: every input pattern becomes the concatenation of the frames
+    // t-left .. t+right of its sequence, the first / last frame repeated at the edges (DataSet.cpp:302-304, 348-363);
+    // --output_time_lag: the target of frame t is the target of frame t-lag, class 0 / value 1 for t < lag (:370-393)
+    void setContext(int left, int right, int outputTimeLag);
+    int fractionInputPatternSize() const { return m_inputPatternSize * (m_contextLeft + m_contextRight + 1); }
     // per-output statistics from the file (outputMeans / outputStdevs), used by --revert_std in forward-pass mode
     void setOutputStatistics(const std::vector<real_t> &means, const std::vector<real_t> &stdevs) { m_outputMeans = means; m_outputStdevs = stdevs; }
     const std::vector<real_t> &outputMeans() const { return m_outputMeans; }
@@ -71,6 +76,7 @@ private:
     int m_curFirstSeqIdx;
     bool m_fractionShuffling, m_sequenceShuffling;
     real_t m_noiseDeviation;
+    int m_contextLeft = 0, m_contextRight = 0, m_outputLag = 0;
     std::mt19937 m_shuffleGen, m_noiseGen;
     std::vector<real_t> m_outputMeans, m_outputStdevs;
     std::future<std::shared_ptr<DataSetFraction>> m_pending;

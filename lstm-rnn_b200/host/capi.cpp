@@ -203,6 +203,7 @@ cn_dataset *cn_dataset_load_netcdf(bl_ctx *ctx, const char *path, int parSeq, fl
     return d.release();
     CN_CATCH(nullptr)
 }
+int cn_dataset_set_context(cn_dataset *ds, int left, int right, int lag) { CN_TRY ds->ds->setContext(left, right, lag); return 0; CN_CATCH(1) }
 void cn_dataset_destroy(cn_dataset *ds) { delete ds; }
 int cn_dataset_info(const cn_dataset *ds, long *o)
 {

@@ -210,9 +210,7 @@ int run(const Options &opt)
     if (opt.str("optimizer") != "steepest_descent") throw std::runtime_error("Unknown optimizer type");
     // reference features outside the B200 hot path are refused rather than silently ignored
     if (opt.num("weight_noise_sigma") != 0) throw std::runtime_error("--weight_noise_sigma is not supported");
-    if (opt.num("input_left_context") != 0 || opt.num("input_right_context") != 0) throw std::runtime_error("--input_left_context / --input_right_context are not supported");
     if (!opt.str("continue").empty()) throw std::runtime_error("--continue is not supported");
-    if (training && opt.num("output_time_lag") != 0) throw std::runtime_error("--output_time_lag is only supported in forward-pass mode");
 
     Ctx ctx;
     if (bl_ctx_create(localRank, nullptr, &ctx.p)) throw std::runtime_error(std::string("bl_ctx_create: ") + bl_last_error(nullptr));
@@ -256,6 +254,8 @@ int run(const Options &opt)
         // only the training set is sorted / truncated / shuffled / noised (main.cpp:585-640)
         std::unique_ptr<data_sets::DataSet> ds = data_sets::loadNetCdfDataSet(ctx.p, files, parallelSequences, fracKey ? (real_t)opt.num(fracKey) : 1,
                                                                               train ? truncSeq : 0, train, rank, world);
+        // context windows and the target lag apply to every set (the reference reads them from the Configuration singleton)
+        ds->setContext((int)opt.num("input_left_context"), (int)opt.num("input_right_context"), (int)opt.num("output_time_lag"));
         if (train) {
             ds->setShuffling(opt.flag("shuffle_fractions"), opt.flag("shuffle_sequences"), blob.seed);
             ds->setInputNoise((real_t)opt.num("input_noise_sigma"), blob.seed);
@@ -284,7 +284,9 @@ int run(const Options &opt)
     const data_sets::DataSet *shapeSet = training ? trainingSet.get() : feedForwardSet.get();
 
     if (chief) { std::printf("Creating the neural network... "); std::fflush(stdout); }
-    NeuralNetwork neuralNetwork(ctx.p, netDoc, parallelSequences, maxSeqLength, shapeSet->inputPatternSize(), shapeSet->outputPatternSize());
+    // the input layer takes the spliced pattern size (the reference passes the unspliced size here, main.cpp:148-152, which makes
+    // its own context options fail in InputLayer::loadSequences; the spliced size is what the fractions carry)
+    NeuralNetwork neuralNetwork(ctx.p, netDoc, parallelSequences, maxSeqLength, shapeSet->fractionInputPatternSize(), shapeSet->outputPatternSize());
     for (data_sets::DataSet *d : {trainingSet.get(), validationSet.get(), testSet.get()})
         if (d && !d->empty() && d->outputPatternSize() != neuralNetwork.postOutputLayer().size())
             throw std::runtime_error("Post output layer size != target pattern size of the data set");

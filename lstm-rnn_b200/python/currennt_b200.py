@@ -108,6 +108,7 @@ def libs():
         h.cn_dataset_create.argtypes = [vp, ci, ip, ci, ci, fp, ip, fp, ci, ci, ci, ci, ci]
         h.cn_dataset_load_netcdf.restype = vp
         h.cn_dataset_load_netcdf.argtypes = [vp, cp, ci, cf, ci, ci, ci, ci]
+        h.cn_dataset_set_context.argtypes = [vp, ci, ci, ci]
         h.cn_dataset_destroy.argtypes = [vp]
         h.cn_dataset_info.argtypes = [vp, lp]
         h.cn_dataset_sequence_lengths.argtypes = [vp, ip, ci]
@@ -269,6 +270,10 @@ class DataSet:
         self.total_sequences, self.total_timesteps, self.min_len, self.max_len, self.num_fractions, c = [int(x) for x in info]
         self.classification = bool(c)
         return self
+
+    def set_context(self, left, right, output_time_lag=0):
+        if self.h.cn_dataset_set_context(self.p, left, right, output_time_lag):
+            raise _herr(self.h)
 
     def sequence_lengths(self):
         out = np.zeros(self.total_sequences, np.int32)

@@ -168,6 +168,25 @@ def test_cli_rejects_what_it_does_not_implement(tmp_path):
     assert r.returncode == 2 and "FAILED" in r.stdout
 
 
+def test_cli_context_windows_and_random_init(tmp_path):
+    """--input_left_context/--input_right_context widen the input layer to (l+r+1) x inputPattSize; without a weights section the
+    weights are drawn from --weights_dist with --random_seed, reproducibly."""
+    cfg, train, val, weights = _setup(tmp_path)
+    json.dump(json.loads(cfg["net"]), open(tmp_path / "plain.jsn", "w"))
+    args = ["--network", "plain.jsn", "--train", "true", "--train_file", "train.nc", "--val_file", "val.nc", "--stochastic", "true",
+            "--parallel_sequences", "8", "--learning_rate", "1e-4", "--max_epochs", "1", "--input_left_context", "1", "--input_right_context", "1",
+            "--output_time_lag", "1", "--weights_dist", "normal", "--weights_normal_sigma", "0.05", "--random_seed", "11"]
+    out1 = _run(args + ["--save_network", "a.jsn"], str(tmp_path))
+    out2 = _run(args + ["--save_network", "b.jsn"], str(tmp_path))
+    assert "(0) input [size: 117]" in out1
+    rows = _epoch_rows(out1)
+    assert len(rows) == 1 and 90.0 < rows[0][1] <= 100.0 and 3.0 < rows[0][2] / 1.0      # untrained 51-class net: ~98 % error, CE ~ T*ln 51 per sequence
+    (_, wa), (_, wb) = _saved_weights(tmp_path / "a.jsn"), _saved_weights(tmp_path / "b.jsn")
+    assert wa.keys() == wb.keys() and all(np.array_equal(wa[k], wb[k]) for k in wa)       # same seed, same run
+    first = json.loads(cfg["net"])["layers"][1]["name"]
+    assert abs(float(np.std(wa[first][:4 * 10 * 117])) - 0.05) < 0.01                     # N(0, 0.05) input weights of the widened first layer
+
+
 def test_cli_data_parallel_two_processes(oracle, tmp_path):
     """Two processes x S=5 train like one process x S=10 (sum of gradients over the global fraction)."""
     import torch

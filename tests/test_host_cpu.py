@@ -121,3 +121,36 @@ def test_data_parallel_sharding_covers_global_fraction(oracle):
         assert sum(f.valid_frames for f in fr) == int(lens[first:first + S * W].sum())
         first += S * W
     assert all(d.next_fraction() is None for d in shards)
+
+
+def test_context_windows_and_output_time_lag():
+    """--input_left_context / --input_right_context splice neighbouring frames (edges repeat the first / last frame) and
+    --output_time_lag shifts the targets (class 0 / value 1.0 before the lag), DataSet.cpp:302-305, 348-393."""
+    S, P, left, right, lag = 3, 4, 2, 1, 2
+    for classification in (True, False):
+        O = 5 if classification else 4
+        (xs, cs, ts), lens = _dataset(5, 9, P, O if classification else 0)
+        ds = cb.DataSet(None, xs, S, seq_classes=cs if classification else None, seq_targets=None if classification else ts, O=O, training=False)
+        ds.set_context(left, right, lag)
+        first = 0
+        while True:
+            f = ds.next_fraction()
+            if f is None:
+                break
+            inputs, pat, tc, tg, sl = f.arrays(classification)
+            ctx = left + right + 1
+            assert inputs.shape[-1] == P * ctx
+            inputs = inputs.reshape(f.T, S, ctx, P)
+            for i in range(f.num_seqs):
+                x, n = xs[first + i], len(xs[first + i])
+                for t in range(n):
+                    for k, off in enumerate(range(-left, right + 1)):
+                        assert np.array_equal(inputs[t, i, k], x[min(max(t + off, 0), n - 1)])
+                    if classification:
+                        assert tc.reshape(f.T, S)[t, i] == (cs[first + i][t - lag] if t >= lag else 0)
+                    else:
+                        want = ts[first + i][t - lag] if t >= lag else np.ones(O, np.float32)
+                        assert np.array_equal(tg.reshape(f.T, S, O)[t, i], want)
+                assert not inputs[n:, i].any()
+            first += S
+        assert first >= len(xs)
