@@ -81,6 +81,13 @@ __device__ __forceinline__ void rg_wait(const unsigned *flag, unsigned target)
     if (threadIdx.x == 0) { while (rg_ld_acquire(flag) < target) { } }
     __syncthreads();
 }
+// per-warp variant: lane 0 of every warp polls, so the exchange copy can start without a CTA barrier in between (the copy is
+// followed by one anyway)
+__device__ __forceinline__ void rg_wait_warp(const unsigned *flag, unsigned target)
+{
+    if ((threadIdx.x & 31) == 0) { while (rg_ld_acquire(flag) < target) { } }
+    __syncwarp();
+}
 __device__ __forceinline__ void rg_publish(unsigned *flag)
 {
     __syncthreads();
@@ -226,7 +233,7 @@ __global__ void __launch_bounds__(RG_NT, 1) lstm_fwd_reg_kernel(const RecFwdPara
         long long *tr = p.trace ? p.trace + ((size_t)blockIdx.x * T + q) * 6 : nullptr;
         if (tr && tid == 0) tr[0] = clock64();
         if (!first) {
-            rg_wait(flag, (unsigned)(g.C * q));
+            rg_wait_warp(flag, (unsigned)(g.C * q));
             if (tr && tid == 0) tr[1] = clock64();
             const float4 *src = reinterpret_cast<const float4 *>(p.hx + ((size_t)(d * 2 + ((q - 1) & 1)) * S + s0) * g.RS);
             float4 *dst = reinterpret_cast<float4 *>(tile);
@@ -383,7 +390,7 @@ __global__ void __launch_bounds__(RG_NT, 1) lstm_bwd_reg_kernel(const RecBwdPara
         }
 
         if (!firstCall) {
-            rg_wait(flag, (unsigned)(g.C * q));
+            rg_wait_warp(flag, (unsigned)(g.C * q));
             const float4 *src = reinterpret_cast<const float4 *>(p.dx + ((size_t)(d * 2 + ((q - 1) & 1)) * S + s0) * g.RS);
             float4 *dst = reinterpret_cast<float4 *>(tile);
             const int n4 = nseq * g.RS / 4;
