@@ -119,7 +119,9 @@ int bl_lstm_forward(bl_lstm_plan *plan, const float *W, const float *X, int ldx,
 /* dY [T*S][lddy] this layer's outputErrors (for the unidirectional layer it is updated in place with the
  * recurrent error terms, as the reference's vector swap does, LstmLayer.cu:907-910); dX [T*S][lddx] =
  * preceding layer's outputErrors or NULL when that layer is not trainable (LstmLayer.cu:991-992);
- * dW = weightUpdates (gradient sums, same layout as W).  Must follow bl_lstm_forward on the same fraction. */
+ * dW = weightUpdates (gradient sums, same layout as W).  Must follow bl_lstm_forward on the same fraction: X, Y and the
+ * input weights must still hold what the forward pass read and wrote (the tensor-core path reuses the forward pass's
+ * TF32 split of X when the same X pointer, ldx and T are passed). */
 int bl_lstm_backward(bl_lstm_plan *plan, const float *W, const float *X, int ldx, const float *Y, int ldy,
                      float *dY, int lddy, const char *patTypes, int T, int Tmin,
                      float *dX, int lddx, float *dW);
