@@ -21,6 +21,7 @@
 #include "gemm_tc.cuh"
 #include <cuda.h>
 #include <cstdint>
+#include <algorithm>
 #include <cstdlib>
 
 namespace bl {
@@ -36,6 +37,7 @@ struct GemmTcParams {
     int batches, mt_per_batch;               // grid.y = batches * mt_per_batch: batch b multiplies A rows [b*a_batch_rows, +M) by the same B
     int a_batch_rows; long long c_batch_stride;   // and writes its [M x N] block at C + b*c_batch_stride
     int kblocks_per_split;
+    int tiles_x, tiles_y, tiles_z;           // persistent 2-CTA kernel: tile grid (n tiles, batches * m tiles, k splits)
     int accumulate;
     float *partial; int ldp;                 // split-K: slice z at partial + z*M*ldp
 };
@@ -323,6 +325,15 @@ __device__ __forceinline__ void umma_commit_2cta(uint64_t *bar)       // arrives
                  :: "r"(smem_u32(bar)), "h"((uint16_t)3) : "memory");
 }
 
+__device__ __forceinline__ void mbar_arrive_remote(uint64_t *bar, uint32_t cta)        // arrive on the same-offset barrier of CTA `cta` of the cluster
+{
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" :: "r"(map_to_cta(smem_u32(bar), cta)) : "memory");
+}
+
+// Persistent: one CTA pair per SM pair walks the output tiles (tile = pair + i * pairs).  TMEM holds TWO 256-column accumulators,
+// so the epilogue of tile i (TMEM -> registers -> shared transpose -> global) overlaps the main loop of tile i+1; the TMA/MMA
+// ring keeps running across tile boundaries.  acc_full[b] (MMA -> both epilogues, multicast commit) and acc_empty[b] (the 8
+// epilogue warps of the pair -> the leader's MMA warp) hand the accumulators back and forth.
 template <bool STRICT, int STAGES>
 __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tf32_tcgen05_2cta_kernel(const __grid_constant__ GemmTcParams p)
 {
@@ -333,20 +344,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tf32_tcgen05_2cta_kernel(c
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint64_t *full = reinterpret_cast<uint64_t *>(smem + STAGES * STAGE_BYTES);
     uint64_t *empty = full + STAGES;
-    uint64_t *tmem_full = empty + STAGES;
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tmem_full + 1);
+    uint64_t *acc_full = empty + STAGES;                                  // [2]
+    uint64_t *acc_empty = acc_full + 2;                                   // [2], used in the leader CTA
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(acc_empty + 2);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t rank = cluster_ctarank();
-    const int batch = blockIdx.y / p.mt_per_batch;
-    const int n0 = (blockIdx.x >> 1) * BN2;
-    const int m0 = (blockIdx.y - batch * p.mt_per_batch) * 2 * TC_BM + (int)rank * TC_BM;   // this CTA's first row inside the batch's block
-    const int a_row0 = batch * p.a_batch_rows + m0;
-    const int b_row0 = n0 + (int)rank * BNH;
+    const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
     const int kb_total = (p.K + TC_BK - 1) / TC_BK;
-    const int kb_begin = blockIdx.z * p.kblocks_per_split;
-    const int kb_end = min(kb_total, kb_begin + p.kblocks_per_split);
-    const int nkb = kb_end - kb_begin;
+    const int tiles_xy = p.tiles_x * p.tiles_y, ntiles = tiles_xy * p.tiles_z;
 
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" :: "l"(&p.tmA) : "memory");
@@ -358,11 +364,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tf32_tcgen05_2cta_kernel(c
     }
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-        mbar_init(tmem_full, 1);
+        for (int b = 0; b < 2; ++b) { mbar_init(&acc_full[b], 1); mbar_init(&acc_empty[b], 8); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 2) {
-        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(tmem_slot)), "n"(BN2) : "memory");
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(tmem_slot)), "n"(2 * BN2) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -370,6 +376,17 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tf32_tcgen05_2cta_kernel(c
     cluster_sync_all();                                                   // the peer's barriers are initialised before anything signals them
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = *tmem_slot;
+
+    // tile -> (n tile, (batch, m tile), k split), the same enumeration the one-tile-per-cluster launch used as its grid
+    auto tile_coords = [&](int tile, int &n0, int &m0, int &batch, int &z, int &kb_begin, int &nkb) {
+        z = tile / tiles_xy;
+        const int r = tile - z * tiles_xy, y = r / p.tiles_x, x = r - y * p.tiles_x;
+        batch = y / p.mt_per_batch;
+        n0 = x * BN2;
+        m0 = (y - batch * p.mt_per_batch) * 2 * TC_BM + (int)rank * TC_BM;
+        kb_begin = z * p.kblocks_per_split;
+        nkb = min(kb_total, kb_begin + p.kblocks_per_split) - kb_begin;
+    };
 
     if (warp == 0) {
         // ===== TMA producer (both CTAs) =====
@@ -380,108 +397,124 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tf32_tcgen05_2cta_kernel(c
         const bool is_b = l >= nca; const int chunk = is_b ? l - nca : l;
         const CUtensorMap *map = is_b ? (is_lo ? &p.tmBlo : &p.tmB) : (is_lo ? &p.tmAlo : &p.tmA);
         const int mn_major = is_b ? p.b_mn : p.a_mn;
-        const int mn = (is_b ? b_row0 : a_row0) + (mn_major ? chunk * 32 : 0);
         const int dst_off = (is_lo ? A_BYTES + B_BYTES : 0) + (is_b ? A_BYTES : 0) + (mn_major ? chunk * TC_BK * 128 : 0);
-        for (int i = 0; i < nkb; ++i) {
-            const int s = i % STAGES, round = i / STAGES;
-            if (lane == 0) {
-                mbar_wait(&empty[s], (round & 1) ^ 1);
-                if (rank == 0) mbar_expect_tx(&full[s], 2 * STAGE_BYTES);          // both CTAs' boxes land on the leader's barrier
-            }
-            __syncwarp();
-            if (lane < nload) {
-                const int kc = (kb_begin + i) * TC_BK;
-                uint8_t *dst = smem + s * STAGE_BYTES + dst_off;
-                const uint32_t bar = map_to_cta(smem_u32(&full[s]), 0);
-                if (mn_major) tma_load_2d_2cta(dst, map, bar, mn, kc);
-                else          tma_load_2d_2cta(dst, map, bar, kc, mn);
+        int it = 0;                                                       // ring position, runs on across tiles
+        for (int tile = pair; tile < ntiles; tile += npairs) {
+            int n0, m0, batch, z, kb_begin, nkb;
+            tile_coords(tile, n0, m0, batch, z, kb_begin, nkb);
+            const int mn = (is_b ? n0 + (int)rank * BNH : batch * p.a_batch_rows + m0) + (mn_major ? chunk * 32 : 0);
+            for (int i = 0; i < nkb; ++i, ++it) {
+                const int s = it % STAGES, round = it / STAGES;
+                if (lane == 0) {
+                    mbar_wait(&empty[s], (round & 1) ^ 1);
+                    if (rank == 0) mbar_expect_tx(&full[s], 2 * STAGE_BYTES);      // both CTAs' boxes land on the leader's barrier
+                }
+                __syncwarp();
+                if (lane < nload) {
+                    const int kc = (kb_begin + i) * TC_BK;
+                    uint8_t *dst = smem + s * STAGE_BYTES + dst_off;
+                    const uint32_t bar = map_to_cta(smem_u32(&full[s]), 0);
+                    if (mn_major) tma_load_2d_2cta(dst, map, bar, mn, kc);
+                    else          tma_load_2d_2cta(dst, map, bar, kc, mn);
+                }
             }
         }
     } else if (warp == 1 && rank == 0) {
         // ===== MMA issuer (leader CTA only) =====
         const uint32_t idesc = make_idesc(2 * TC_BM, BN2, p.a_mn, p.b_mn);
         const uint64_t a_step = (uint64_t)(((p.a_mn ? 1024 : TC_UMMA_K * 4)) >> 4), b_step = (uint64_t)(((p.b_mn ? 1024 : TC_UMMA_K * 4)) >> 4);
-        for (int i = 0; i < nkb; ++i) {
-            const int s = i % STAGES, round = i / STAGES;
-            mbar_wait(&full[s], round & 1);
+        int it = 0, lt = 0;                                               // ring position; local tile counter
+        for (int tile = pair; tile < ntiles; tile += npairs, ++lt) {
+            int n0, m0, batch, z, kb_begin, nkb;
+            tile_coords(tile, n0, m0, batch, z, kb_begin, nkb);
+            const int buf = lt & 1;
+            mbar_wait(&acc_empty[buf], ((lt >> 1) & 1) ^ 1);              // both epilogues have drained this accumulator (first use: free)
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            if (elect_one()) {
-                const uint8_t *st = smem + s * STAGE_BYTES;
-                const uint64_t a_hi = make_smem_desc(st, p.a_mn), b_hi = make_smem_desc(st + A_BYTES, p.b_mn);
-                const uint64_t a_lo = make_smem_desc(st + A_BYTES + B_BYTES, p.a_mn), b_lo = make_smem_desc(st + 2 * A_BYTES + B_BYTES, p.b_mn);
+            const uint32_t tmem_d = tmem_base + (uint32_t)(buf * BN2);
+            for (int i = 0; i < nkb; ++i, ++it) {
+                const int s = it % STAGES, round = it / STAGES;
+                mbar_wait(&full[s], round & 1);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                if (elect_one()) {
+                    const uint8_t *st = smem + s * STAGE_BYTES;
+                    const uint64_t a_hi = make_smem_desc(st, p.a_mn), b_hi = make_smem_desc(st + A_BYTES, p.b_mn);
+                    const uint64_t a_lo = make_smem_desc(st + A_BYTES + B_BYTES, p.a_mn), b_lo = make_smem_desc(st + 2 * A_BYTES + B_BYTES, p.b_mn);
 #pragma unroll
-                for (int kk = 0; kk < TC_BK / TC_UMMA_K; ++kk) {
-                    const uint64_t ad = kk * a_step, bd = kk * b_step;
-                    const uint32_t acc0 = (i > 0 || kk > 0) ? 1u : 0u;
-                    if (STRICT) {
-                        umma_tf32_2cta(tmem_base, a_lo + ad, b_hi + bd, idesc, acc0);
-                        umma_tf32_2cta(tmem_base, a_hi + ad, b_lo + bd, idesc, 1u);
-                        umma_tf32_2cta(tmem_base, a_hi + ad, b_hi + bd, idesc, 1u);
-                    } else {
-                        umma_tf32_2cta(tmem_base, a_hi + ad, b_hi + bd, idesc, acc0);
+                    for (int kk = 0; kk < TC_BK / TC_UMMA_K; ++kk) {
+                        const uint64_t ad = kk * a_step, bd = kk * b_step;
+                        const uint32_t acc0 = (i > 0 || kk > 0) ? 1u : 0u;
+                        if (STRICT) {
+                            umma_tf32_2cta(tmem_d, a_lo + ad, b_hi + bd, idesc, acc0);
+                            umma_tf32_2cta(tmem_d, a_hi + ad, b_lo + bd, idesc, 1u);
+                            umma_tf32_2cta(tmem_d, a_hi + ad, b_hi + bd, idesc, 1u);
+                        } else {
+                            umma_tf32_2cta(tmem_d, a_hi + ad, b_hi + bd, idesc, acc0);
+                        }
                     }
+                    umma_commit_2cta(&empty[s]);
+                    if (i == nkb - 1) umma_commit_2cta(&acc_full[buf]);
                 }
-                umma_commit_2cta(&empty[s]);
-                if (i == nkb - 1) umma_commit_2cta(tmem_full);
+                __syncwarp();
             }
-            __syncwarp();
         }
     } else if (warp >= 4) {
-        // ===== epilogue (both CTAs): own 128 rows x 256 columns =====
+        // ===== epilogue (both CTAs): own 128 rows x 256 columns of every tile of the pair =====
         // tcgen05.ld hands lane r the 32 consecutive columns of row r; storing that directly makes every warp store touch 32
         // different 128 B lines with 16 B each.  Each warp instead transposes its 32 x 32 block through a private shared
         // tile so that one store instruction writes 4 complete 128 B lines.
         const int ew = warp & 3;
         float *stg = reinterpret_cast<float *>(smem + STAGES * STAGE_BYTES + 256) + ew * (32 * EPI_LD);
-        const int row_base = m0 + ew * 32;
-        if (nkb > 0) {
-            mbar_wait(tmem_full, 0);
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        }
-        float *out = p.partial ? p.partial + ((size_t)blockIdx.z * p.batches + batch) * p.M * p.ldp : p.C + (size_t)batch * p.c_batch_stride;
-        const int ldo = p.partial ? p.ldp : p.ldc;
-        const bool acc = (!p.partial) && p.accumulate;
-        const bool vec_ok = ((ldo & 3) == 0) && ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
         const int sub_r = lane >> 3, sub_c = (lane & 7) * 4;              // this lane's row (within a group of 4) and first column when storing
+        int lt = 0;
+        for (int tile = pair; tile < ntiles; tile += npairs, ++lt) {
+            int n0, m0, batch, z, kb_begin, nkb;
+            tile_coords(tile, n0, m0, batch, z, kb_begin, nkb);
+            const int buf = lt & 1;
+            const int row_base = m0 + ew * 32;
+            mbar_wait(&acc_full[buf], (lt >> 1) & 1);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            float *out = p.partial ? p.partial + ((size_t)z * p.batches + batch) * p.M * p.ldp : p.C + (size_t)batch * p.c_batch_stride;
+            const int ldo = p.partial ? p.ldp : p.ldc;
+            const bool acc = (!p.partial) && p.accumulate;
+            const bool vec_ok = ((ldo & 3) == 0) && ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
 #pragma unroll 1
-        for (int c = 0; c < BN2; c += 32) {
-            if (n0 + c >= p.N) break;
-            float v[32];
-            if (nkb > 0) {
-                tmem_ld32(tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)c, v);
-            } else {
+            for (int c = 0; c < BN2; c += 32) {
+                if (n0 + c >= p.N) break;
+                float v[32];
+                tmem_ld32(tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(buf * BN2 + c), v);
 #pragma unroll
-                for (int i = 0; i < 32; ++i) v[i] = 0.0f;
-            }
+                for (int i = 0; i < 32; i += 4) *reinterpret_cast<float4 *>(stg + lane * EPI_LD + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+                __syncwarp();
+                const int col = n0 + c + sub_c;
 #pragma unroll
-            for (int i = 0; i < 32; i += 4) *reinterpret_cast<float4 *>(stg + lane * EPI_LD + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
-            __syncwarp();
-            const int col = n0 + c + sub_c;
+                for (int it = 0; it < 8; ++it) {
+                    const int r = it * 4 + sub_r, row = row_base + r;
+                    if (row >= p.M) continue;
+                    float4 o = *reinterpret_cast<const float4 *>(stg + r * EPI_LD + sub_c);
+                    float *dst = out + (size_t)row * ldo + col;
+                    if (vec_ok && col + 4 <= p.N) {
+                        if (acc) { const float4 old = *reinterpret_cast<const float4 *>(dst); o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w; }
+                        *reinterpret_cast<float4 *>(dst) = o;
+                    } else {
+                        const float e[4] = {o.x, o.y, o.z, o.w};
 #pragma unroll
-            for (int it = 0; it < 8; ++it) {
-                const int r = it * 4 + sub_r, row = row_base + r;
-                if (row >= p.M) continue;
-                float4 o = *reinterpret_cast<const float4 *>(stg + r * EPI_LD + sub_c);
-                float *dst = out + (size_t)row * ldo + col;
-                if (vec_ok && col + 4 <= p.N) {
-                    if (acc) { const float4 old = *reinterpret_cast<const float4 *>(dst); o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w; }
-                    *reinterpret_cast<float4 *>(dst) = o;
-                } else {
-                    const float e[4] = {o.x, o.y, o.z, o.w};
-#pragma unroll
-                    for (int i = 0; i < 4; ++i)
-                        if (col + i < p.N) dst[i] = acc ? dst[i] + e[i] : e[i];
+                        for (int i = 0; i < 4; ++i)
+                            if (col + i < p.N) dst[i] = acc ? dst[i] + e[i] : e[i];
+                    }
                 }
+                __syncwarp();
             }
+            // this warp has read its lanes of the accumulator: hand it back to the leader's MMA warp
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             __syncwarp();
+            if (lane == 0) mbar_arrive_remote(&acc_empty[buf], 0);
         }
-        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     }
     __syncthreads();
     cluster_sync_all();                                                   // neither CTA may free TMEM or exit while the pair is still running
     if (warp == 2) {
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" :: "r"(tmem_base), "n"(BN2) : "memory");
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" :: "r"(tmem_base), "n"(2 * BN2) : "memory");
     }
 }
 
@@ -709,7 +742,13 @@ int tc_gemm_batched(bl_ctx *ctx, int M, int N, int K, const TcView &A, const TcV
     p.batches = batches; p.mt_per_batch = cdiv(M, BMT); p.a_batch_rows = a_batch_mn; p.c_batch_stride = c_batch_stride;
     dim3 grid(cdiv(N, BN) * (pair ? 2 : 1), batches * cdiv(M, BMT), nsplit);
     if (grid.y > 65535) return fail(ctx, "tc_gemm: M too large");
-    if (pair) BL_CHECK((launch_tc_2cta<true, 3>(ctx, p, grid)));
+    p.tiles_x = pair ? (int)grid.x / 2 : (int)grid.x; p.tiles_y = (int)grid.y; p.tiles_z = (int)grid.z;
+    if (pair) {
+        // persistent launch: one CTA pair per SM pair (or per tile when there are fewer tiles)
+        const long long ntiles = (long long)p.tiles_x * p.tiles_y * p.tiles_z;
+        const int pairs = (int)std::min<long long>(ntiles, ctx->num_sms / 2);
+        BL_CHECK((launch_tc_2cta<true, 3>(ctx, p, dim3(2 * pairs, 1, 1))));
+    }
     else if (strict && BN_STRICT == 256) BL_CHECK((launch_tc<256, true, 2>(ctx, p, grid)));
     else if (strict) BL_CHECK((launch_tc<128, true, 3>(ctx, p, grid)));
     else        BL_CHECK((launch_tc<BN_FAST, false, 4>(ctx, p, grid)));
