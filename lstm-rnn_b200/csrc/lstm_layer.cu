@@ -35,6 +35,7 @@ struct bl_lstm_plan {
     size_t tc_eX, tc_eWf, tc_eD, tc_eY, tc_eWb;
     bl::TcOperand xsplit;    // strict split of the forward pass's X, reused by the backward pass of the same fraction
     const float *xsplit_src; int xsplit_ld, xsplit_T;
+    int ysplit_T;            // T of the fraction whose Y split the forward kernel wrote into tc_Y (0 = none)
     unsigned *flags_f, *flags_b;
     int gsplit;
     int lastT;
@@ -122,7 +123,7 @@ int bl_lstm_plan_create(bl_ctx *ctx, int P, int L, int bidirectional, int S, int
     pl->flags_f = pl->flags_b = nullptr;
     pl->trace = nullptr;
     pl->tcbuf = nullptr; pl->tcbuf_elems = 0;
-    pl->xsplit_src = nullptr; pl->xsplit_ld = 0; pl->xsplit_T = 0;
+    pl->xsplit_src = nullptr; pl->xsplit_ld = 0; pl->xsplit_T = 0; pl->ysplit_T = 0;
 
     const int cap = ctx->smem_optin - 2048;      // room for the kernels' static shared memory (exp table) and the driver's reserve
     // tuning overrides (tools/sweep_geometry.py): sequence groups / sub-CTAs / threads of either kernel, and the kernel family
@@ -198,6 +199,8 @@ static int plan_tc_buffers(bl_lstm_plan *pl)
     (void)nb;
     const size_t need = 2 * (pl->tc_eX + pl->tc_eWf + pl->tc_eD + pl->tc_eY + pl->tc_eWb) + 16;
     BL_CUDA(ctx, cudaMalloc(&pl->tcbuf, need * sizeof(float)));
+    // the re-blocking pad columns of the splits the recurrent kernels write directly are never touched again: zero them once
+    BL_CUDA(ctx, cudaMemsetAsync(pl->tcbuf, 0, need * sizeof(float), ctx->stream));
     pl->tcbuf_elems = need;
     float *b = reinterpret_cast<float *>((reinterpret_cast<uintptr_t>(pl->tcbuf) + 15) & ~(uintptr_t)15);
     pl->tc_X = b; b += 2 * pl->tc_eX;
@@ -235,6 +238,14 @@ int bl_lstm_forward(bl_lstm_plan *pl, const float *W, const float *X, int ldx, c
     p.Wb = W + (size_t)4 * L * P; p.Wi = p.Wb + 4 * L; p.Wp = p.Wi + (size_t)4 * L * H;
     p.acts = pl->acts; p.cst = pl->cst; p.Y = Y; p.ldy = ldy; p.hx = pl->hx; p.flags = pl->flags_f; p.pat = patTypes;
     p.T = T; p.Tmin = Tmin; p.S = S; p.H = H; p.L = L; p.ndir = pl->ndir; p.bias = pl->bias; p.g = pl->gf; p.trace = pl->trace;
+    // the tensor-core backward pass wants the TF32 split of Y: the register-resident kernel writes it while it stores Y
+    p.ys_hi = p.ys_lo = nullptr; p.ld_ys = 0;
+    pl->ysplit_T = 0;
+    if (pl->reg_f && bl::tc_wanted(ctx, P, 4 * L, N) && getenv("BLSTM_NO_FUSED_SPLIT") == nullptr) {
+        BL_CHECK(plan_tc_buffers(pl));
+        p.ys_hi = pl->tc_Y; p.ys_lo = pl->tc_Y + pl->tc_eY; p.ld_ys = (int)bl::tc_operand_ld(pl->ndir * ((H + 3) & ~3));
+        pl->ysplit_T = T;
+    }
     BL_CHECK(pl->reg_f ? bl::launch_lstm_fwd_reg(ctx, p) : bl::launch_lstm_fwd(ctx, p));
     pl->lastT = T;
     return 0;
@@ -258,9 +269,16 @@ int bl_lstm_backward(bl_lstm_plan *pl, const float *W, const float *X, int ldx, 
     p.acts = pl->acts; p.cst = pl->cst; p.deltas = pl->deltas; p.cerr = pl->cerr; p.dY = dY; p.lddy = lddy;
     p.dx = pl->dx; p.flags = pl->flags_b; p.pat = patTypes;
     p.T = T; p.Tmin = Tmin; p.S = S; p.H = H; p.L = L; p.ndir = pl->ndir; p.g = pl->gb;
+    const bool tc = bl::tc_wanted(ctx, P, 4 * L, N);
+    const bool fused_dsplit = tc && pl->reg_b && getenv("BLSTM_NO_FUSED_SPLIT") == nullptr;
+    p.ds_hi = p.ds_lo = nullptr; p.ld_ds = 0;
+    if (fused_dsplit) {
+        BL_CHECK(plan_tc_buffers(pl));
+        p.ds_hi = pl->tc_D; p.ds_lo = pl->tc_D + pl->tc_eD; p.ld_ds = (int)bl::tc_operand_ld(4 * pl->ndir * ((H + 3) & ~3));
+    }
     BL_CHECK(pl->reg_b ? bl::launch_lstm_bwd_reg(ctx, p) : bl::launch_lstm_bwd(ctx, p));
 
-    if (bl::tc_wanted(ctx, P, 4 * L, N)) {
+    if (tc) {
         // ---- tensor-core path: every operand is split (hi/lo TF32) ONCE per layer, in its own row-major layout, and read
         // either K-major or MN-major by the GEMMs -- nothing is transposed in memory.  The (gate, direction) blocks of H
         // cells are re-pitched to Hp = roundup(H, 4) so that block sub-views start on 16-byte boundaries:
@@ -272,10 +290,16 @@ int bl_lstm_backward(bl_lstm_plan *pl, const float *W, const float *X, int ldx, 
         const int nb = 4 * pl->ndir, Hp = (H + 3) & ~3;
         BL_CHECK(plan_tc_buffers(pl));
         bl::TcOperand D, Xs, Ys, Ws;
-        BL_CHECK(bl::tc_prepare(ctx, pl->deltas, N, 4 * L, 4 * L, strict, pl->tc_D, pl->tc_D + pl->tc_eD, &D, 0, 0, H, Hp));
+        if (fused_dsplit) {       // written by the BPTT kernel
+            D.hi = pl->tc_D; D.lo = pl->tc_D + pl->tc_eD; D.ld = (size_t)p.ld_ds; D.rows = N; D.cols = nb * Hp; D.strict = true;
+        } else
+            BL_CHECK(bl::tc_prepare(ctx, pl->deltas, N, 4 * L, 4 * L, strict, pl->tc_D, pl->tc_D + pl->tc_eD, &D, 0, 0, H, Hp));
         if (pl->xsplit_src == X && pl->xsplit_ld == ldx && pl->xsplit_T == T) Xs = pl->xsplit;
         else BL_CHECK(bl::tc_prepare(ctx, X, N, P, ldx, strict, pl->tc_X, pl->tc_X + pl->tc_eX, &Xs));
-        BL_CHECK(bl::tc_prepare(ctx, Y, N, L, ldy, strict, pl->tc_Y, pl->tc_Y + pl->tc_eY, &Ys, 0, 0, H, Hp));
+        if (pl->ysplit_T == T) {  // written by the forward kernel of this fraction
+            Ys.hi = pl->tc_Y; Ys.lo = pl->tc_Y + pl->tc_eY; Ys.ld = bl::tc_operand_ld(pl->ndir * Hp); Ys.rows = N; Ys.cols = pl->ndir * Hp; Ys.strict = true;
+        } else
+            BL_CHECK(bl::tc_prepare(ctx, Y, N, L, ldy, strict, pl->tc_Y, pl->tc_Y + pl->tc_eY, &Ys, 0, 0, H, Hp));
         // (2) error to the preceding layer: dX[N][P] = deltas[N][4L] * Win[4L][P]   (the 8 products of :996-1006)
         if (dX) {
             BL_CHECK(bl::tc_prepare(ctx, W, 4 * L, P, P, strict, pl->tc_Wb, pl->tc_Wb + pl->tc_eWb, &Ws, H, Hp, 0, 0));

@@ -42,6 +42,9 @@ struct RecFwdParams {
     int T, Tmin, S, H, L, ndir;
     float bias;
     long long *trace;               // optional [CTAs*nsub][T][6] clock64 stamps (BLSTM_REC_TRACE tuning aid), else NULL
+    // optional (register-resident kernels only): TF32 split of the layer output written on the fly for the tensor-core backward
+    // pass, hi/lo [N][ld_ys], column d*Hq + j with Hq = roundup(H, 4); NULL = not wanted
+    float *ys_hi, *ys_lo; int ld_ys;
     RecGeom g;
 };
 
@@ -55,6 +58,8 @@ struct RecBwdParams {
     unsigned *flags;
     const char *pat;
     int T, Tmin, S, H, L, ndir;
+    // optional (register-resident kernels only): TF32 split of the deltas, hi/lo [N][ld_ds], column (gate*ndir + d)*Hq + j
+    float *ds_hi, *ds_lo; int ld_ds;
     RecGeom g;
 };
 

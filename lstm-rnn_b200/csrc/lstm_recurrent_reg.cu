@@ -10,6 +10,7 @@
 // fall into different banks:  koff(k) = (k >> 5) * 36 + (k & 31).
 #include "lstm_recurrent.cuh"
 #include <cmath>
+#include <cstdint>
 
 namespace bl {
 
@@ -146,6 +147,16 @@ __device__ __forceinline__ float rg_stage_sum(const float *sp, int KSn, int kstr
     for (; ks + 1 < KSn; ks += 2) { s0 += sp[ks * kstride]; s1 += sp[(ks + 1) * kstride]; }
     if (ks < KSn) s0 += sp[ks * kstride];
     return s0 + s1;
+}
+
+// hi = tf32_rna(x), lo = x - hi (exact): the operand split of the strict tensor-core GEMMs (gemm_tc.cu), produced here so that the
+// backward pass needs no separate split pass over the deltas / layer outputs
+__device__ __forceinline__ void rg_split_store(float *hi, float *lo, size_t idx, float v)
+{
+    uint32_t h;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h) : "f"(v));
+    hi[idx] = __uint_as_float(h);
+    lo[idx] = __fsub_rn(v, __uint_as_float(h));
 }
 
 // ------------------------------------------------------------------------------------------------ forward
@@ -295,6 +306,7 @@ __global__ void __launch_bounds__(RG_NT, 1) lstm_fwd_reg_kernel(const RecFwdPara
             }
             cst_t[slot * L + cl] = cprev[u];
             y_t[slot * p.ldy + cl] = r_h[u];
+            if (p.ys_hi) rg_split_store(p.ys_hi, p.ys_lo, ((size_t)t * S + slot) * p.ld_ys + d * ((H + 3) & ~3) + j0 + cl, r_h[u]);
         }
         if (tr && tid == 0) tr[5] = clock64();
     }
@@ -440,6 +452,12 @@ __global__ void __launch_bounds__(RG_NT, 1) lstm_bwd_reg_kernel(const RecBwdPara
             float *dp = del_t + slot * 4 * L + cl;
             dp[0] = r_dni[u]; dp[L] = ndig[u]; dp[2 * L] = ndfg[u]; dp[3 * L] = r_dog[u];
             cerr_t[slot * L + cl] = ncerr[u];
+            if (p.ds_hi) {
+                const int Hq = (H + 3) & ~3;
+                const size_t base = ((size_t)t * S + slot) * p.ld_ds + (size_t)d * Hq + j0 + cl, gs = (size_t)p.ndir * Hq;
+                rg_split_store(p.ds_hi, p.ds_lo, base, r_dni[u]); rg_split_store(p.ds_hi, p.ds_lo, base + gs, ndig[u]);
+                rg_split_store(p.ds_hi, p.ds_lo, base + 2 * gs, ndfg[u]); rg_split_store(p.ds_hi, p.ds_lo, base + 3 * gs, r_dog[u]);
+            }
         }
     }
 }
