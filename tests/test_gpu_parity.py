@@ -332,6 +332,30 @@ def test_network_parity_with_tensor_core_gemms(oracle, gpu_ctx):
         gpu_ctx.set_gemm_backend(0)
 
 
+def test_fused_operand_split_is_bit_identical(oracle, gpu_ctx, monkeypatch):
+    """The recurrent kernels write the TF32 hi/lo split of deltas and outputs while they store them; the separate split pass
+    (BLSTM_NO_FUSED_SPLIT=1) must give bit-identical gradients -- both feed the same words to the same GEMMs."""
+    import currennt_b200 as cb
+    net_json = synth.network_json(37, [126, ("lstm", 50)], 21)
+    lengths = [3, 8, 11, 11, 14]
+    weights, frac = small_case(oracle, net_json, 5, lengths, seed=8, classes=21, target_size=0)
+    gpu_ctx.set_gemm_backend(2)
+    try:
+        runs = []
+        for fused in (True, False):
+            if fused:
+                monkeypatch.delenv("BLSTM_NO_FUSED_SPLIT", raising=False)
+            else:
+                monkeypatch.setenv("BLSTM_NO_FUSED_SPLIT", "1")
+            net = cb.Net(gpu_ctx, net_json, 5, max(lengths) + 2)
+            run_net(net, weights, frac)
+            runs.append([net.get_weight_updates(i) for i in (1, 2)] + [net.get_output_errors(1)])
+        for a, b in zip(*runs):
+            assert np.array_equal(a, b)
+    finally:
+        gpu_ctx.set_gemm_backend(0)
+
+
 # ----------------------------------------------------------------------------- BASELINE.json configs at (or near) full size
 def _full_net(gpu_ctx, name, S, maxT):
     import currennt_b200 as cb
