@@ -154,3 +154,22 @@ def test_context_windows_and_output_time_lag():
                 assert not inputs[n:, i].any()
             first += S
         assert first >= len(xs)
+
+
+def test_command_line_front_end_without_gpu(tmp_path):
+    """Option parsing is host-only; anything that would compute needs a device and says so (no CPU path)."""
+    import subprocess
+    exe = os.path.join(ROOT, "lstm-rnn_b200", "currennt_b200")
+    if not os.path.exists(exe):
+        pytest.skip("driver not built")
+    r = subprocess.run([exe, "--help"], capture_output=True, text=True)
+    assert r.returncode == 0 and "--parallel_sequences" in r.stdout and "--truncate_seq" in r.stdout and "--train_file" in r.stdout
+    r = subprocess.run([exe, "--bogus", "1"], capture_output=True, text=True)
+    assert r.returncode == 1 and "unrecognised option 'bogus'" in r.stderr
+    (tmp_path / "c.cfg").write_text("train = true\nnot a key value line\n")
+    r = subprocess.run([exe, "--options_file", str(tmp_path / "c.cfg")], capture_output=True, text=True)
+    assert r.returncode == 1 and "options file" in r.stderr
+    import torch
+    if not torch.cuda.is_available():
+        r = subprocess.run([exe, "--train", "true", "--train_file", "x.nc"], capture_output=True, text=True)
+        assert r.returncode == 2 and "FAILED" in r.stdout and "no CPU fallback" in r.stdout
