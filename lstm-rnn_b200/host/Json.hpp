@@ -19,6 +19,7 @@ public:
     static JsonValue makeObject() { JsonValue v; v.m_type = Object; return v; }
     static JsonValue makeNumber(double d, bool isInt = false) { JsonValue v; v.m_type = Number; v.m_num = d; v.m_isInt = isInt; return v; }
     static JsonValue makeString(const std::string &s) { JsonValue v; v.m_type = String; v.m_str = s; return v; }
+    static JsonValue makeBool(bool b) { JsonValue v; v.m_type = Bool; v.m_bool = b; return v; }
 
     Type type() const { return m_type; }
     bool IsObject() const { return m_type == Object; }
@@ -26,6 +27,8 @@ public:
     bool IsNumber() const { return m_type == Number; }
     bool IsInt()    const { return m_type == Number && m_isInt; }
     bool IsString() const { return m_type == String; }
+    bool IsBool()   const { return m_type == Bool; }
+    bool GetBool() const { return m_bool; }
 
     bool HasMember(const std::string &name) const;
     const JsonValue &operator[](const std::string &name) const;   // throws if missing

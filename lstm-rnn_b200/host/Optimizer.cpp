@@ -172,6 +172,89 @@ bool SteepestDescentOptimizer::train()
     return m_finished;
 }
 
+namespace {
+void exportVectors(helpers::JsonDocument &doc, const char *name, const std::vector<std::unique_ptr<device::real_vector>> &vs)
+{
+    helpers::JsonValue arr = helpers::JsonValue::makeArray();                     // Optimizer.cu:107-122: one array per layer
+    for (const auto &v : vs) {
+        helpers::JsonValue a = helpers::JsonValue::makeArray();
+        const std::vector<real_t> h = v->toHost();
+        a.Reserve(h.size());
+        for (real_t x : h) a.PushBack(helpers::JsonValue::makeNumber(x));
+        arr.PushBack(a);
+    }
+    doc.member(name) = arr;
+}
+
+void importVectors(const helpers::JsonDocument &doc, const char *name, std::vector<std::unique_ptr<device::real_vector>> &vs)
+{
+    if (!doc.HasMember(name) || !doc[name].IsArray())                             // Optimizer.cu:124-150, same messages
+        throw std::runtime_error(std::string("Array '") + name + "' is missing or has the wrong type");
+    if (doc[name].Size() != vs.size()) throw std::runtime_error(std::string("Array '") + name + "' has a wrong size");
+    for (size_t i = 0; i < vs.size(); ++i) {
+        const helpers::JsonValue &a = doc[name].at(i);
+        if (!a.IsArray()) throw std::runtime_error(std::string("Object in '") + name + "' is not an array");
+        if (a.Size() != vs[i]->size()) throw std::runtime_error(std::string("Subarray in '") + name + "' has a wrong size");
+        std::vector<real_t> h(a.Size());
+        for (size_t j = 0; j < h.size(); ++j) h[j] = (real_t)a.at(j).GetDouble();
+        if (!h.empty()) vs[i]->fromHost(h.data(), h.size());
+    }
+}
+
+template <typename T> T checkedGet(const helpers::JsonDocument &doc, const char *name);
+template <> bool checkedGet<bool>(const helpers::JsonDocument &doc, const char *name)
+{
+    if (!doc.HasMember(name) || !doc[name].IsBool()) throw std::runtime_error(std::string("Missing or invalid value '") + name + "'");
+    return doc[name].GetBool();
+}
+template <> int checkedGet<int>(const helpers::JsonDocument &doc, const char *name)
+{
+    if (!doc.HasMember(name) || !doc[name].IsNumber()) throw std::runtime_error(std::string("Missing or invalid value '") + name + "'");
+    return doc[name].GetInt();
+}
+template <> real_t checkedGet<real_t>(const helpers::JsonDocument &doc, const char *name)
+{
+    if (!doc.HasMember(name) || !doc[name].IsNumber()) throw std::runtime_error(std::string("Missing or invalid value '") + name + "'");
+    return (real_t)doc[name].GetDouble();
+}
+} // namespace
+
+void SteepestDescentOptimizer::exportState(helpers::JsonDocument &doc)
+{
+    using helpers::JsonValue;
+    if (m_bestWeights.empty()) storeWeights();                                    // the reference starts with best = initial weights (Optimizer.cu ctor)
+    doc.member("optimizer_finished") = JsonValue::makeBool(m_finished);
+    doc.member("optimizer_cur_epoch") = JsonValue::makeNumber(m_curEpoch, true);
+    doc.member("optimizer_epochs_since_lowest_error") = JsonValue::makeNumber(m_epochsSinceLowestError, true);
+    doc.member("optimizer_lowest_validation_error") = JsonValue::makeNumber(m_lowestValidationError);
+    doc.member("optimizer_cur_training_error") = JsonValue::makeNumber(m_curTrainingError);
+    doc.member("optimizer_cur_validation_error") = JsonValue::makeNumber(m_curValidationError);
+    doc.member("optimizer_cur_test_error") = JsonValue::makeNumber(m_curTestError);
+    doc.member("optimizer_cur_training_class_error") = JsonValue::makeNumber(m_curTrainingClassError);
+    doc.member("optimizer_cur_validation_class_error") = JsonValue::makeNumber(m_curValidationClassError);
+    doc.member("optimizer_cur_test_class_error") = JsonValue::makeNumber(m_curTestClassError);
+    exportVectors(doc, "optimizer_best_weights", m_bestWeights);
+    exportVectors(doc, "steepest_descent_optimizer_weight_deltas", m_weightDeltas);
+}
+
+void SteepestDescentOptimizer::importState(const helpers::JsonDocument &doc)
+{
+    if (m_bestWeights.empty()) storeWeights();                                    // allocates the per-layer vectors
+    m_finished = checkedGet<bool>(doc, "optimizer_finished");
+    m_curEpoch = checkedGet<int>(doc, "optimizer_cur_epoch");
+    m_epochsSinceLowestError = checkedGet<int>(doc, "optimizer_epochs_since_lowest_error");
+    m_lowestValidationError = checkedGet<real_t>(doc, "optimizer_lowest_validation_error");
+    m_curTrainingError = checkedGet<real_t>(doc, "optimizer_cur_training_error");
+    m_curValidationError = checkedGet<real_t>(doc, "optimizer_cur_validation_error");
+    m_curTestError = checkedGet<real_t>(doc, "optimizer_cur_test_error");
+    m_curTrainingClassError = checkedGet<real_t>(doc, "optimizer_cur_training_class_error");
+    m_curValidationClassError = checkedGet<real_t>(doc, "optimizer_cur_validation_class_error");
+    m_curTestClassError = checkedGet<real_t>(doc, "optimizer_cur_test_class_error");
+    importVectors(doc, "optimizer_best_weights", m_bestWeights);
+    importVectors(doc, "steepest_descent_optimizer_weight_deltas", m_weightDeltas);
+    check(m_nn.ctx(), bl_sync(m_nn.ctx()));
+}
+
 std::vector<std::vector<real_t>> SteepestDescentOptimizer::weightDeltasToHost() const
 {
     std::vector<std::vector<real_t>> out;

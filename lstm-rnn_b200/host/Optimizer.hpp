@@ -46,6 +46,11 @@ public:
     real_t curValidationClassError() const { return m_curValidationClassError; }
     real_t curTestClassError() const { return m_curTestClassError; }
 
+    // autosave state in the reference's JSON fields (Optimizer.cu:326-360, SteepestDescentOptimizer.cu:118-131):
+    // epoch counters, current / lowest errors, "optimizer_best_weights" and "steepest_descent_optimizer_weight_deltas"
+    void exportState(helpers::JsonDocument &jsonDoc);
+    void importState(const helpers::JsonDocument &jsonDoc);
+
     real_t learningRate() const { return m_learningRate; }
     void setLearningRate(real_t lr) { m_learningRate = lr; }
     std::vector<std::vector<real_t>> weightDeltasToHost() const;

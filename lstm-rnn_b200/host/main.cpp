@@ -91,6 +91,30 @@ struct Options {
         if (v.count("options_file")) parseFile(v["options_file"]);
         for (const auto &d : defaults()) if (!v.count(d.first)) v[d.first] = d.second;
     }
+    // "key=value;;;..." as stored in autosave files (Configuration.cpp:46-66)
+    std::string serialize() const
+    {
+        std::string s;
+        for (const auto &kv : v) if (kv.first != "continue" && kv.first != "options_file" && kv.first != "help") s += kv.first + '=' + kv.second + ";;;";
+        return s;
+    }
+    // --continue: every option is taken from the autosave file's "configuration" string (Configuration.cpp:68-100, 239-250)
+    void restoreFrom(const std::string &serialized)
+    {
+        const std::string cont = v.count("continue") ? v["continue"] : "";
+        v.clear();
+        size_t pos = 0;
+        while (pos < serialized.size()) {
+            size_t end = serialized.find(";;;", pos);
+            if (end == std::string::npos) end = serialized.size();
+            const std::string item = serialized.substr(pos, end - pos);
+            const size_t eq = item.find('=');
+            if (eq != std::string::npos) set(trim(item.substr(0, eq)), trim(item.substr(eq + 1)), true);
+            pos = end + 3;
+        }
+        for (const auto &d : defaults()) if (!v.count(d.first)) v[d.first] = d.second;
+        v["continue"] = cont;
+    }
     const std::string &str(const std::string &k) const { return v.at(k); }
     double num(const std::string &k) const
     {
@@ -180,6 +204,29 @@ void saveNetwork(const NeuralNetwork &nn, const std::string &filename)          
     f << doc.serialize(true);
 }
 
+std::string replaceAll(std::string s, const std::string &from, const std::string &to)
+{
+    for (size_t pos = 0; (pos = s.find(from, pos)) != std::string::npos; pos += to.size()) s.replace(pos, from.size(), to);
+    return s;
+}
+
+// autosave file: configuration + epoch table + network + optimizer state (main.cpp:702-741); name <prefix>_epochNNN.autosave
+void saveState(const NeuralNetwork &nn, optimizers::SteepestDescentOptimizer &optimizer, const Options &opt, const std::string &infoRows)
+{
+    helpers::JsonDocument doc = helpers::JsonValue::makeObject();
+    doc.member("configuration") = helpers::JsonValue::makeString(opt.serialize());
+    doc.member("info_rows") = helpers::JsonValue::makeString(replaceAll(infoRows, "\n", ";;;"));
+    nn.exportLayers(doc);
+    nn.exportWeights(doc);
+    optimizer.exportState(doc);
+    char name[64]; std::snprintf(name, sizeof name, "epoch%03d.autosave", optimizer.currentEpoch());
+    const std::string prefix = opt.str("autosave_prefix");
+    const std::string path = prefix.empty() ? std::string(name) : prefix + "_" + name;
+    std::ofstream f(path.c_str(), std::ios::binary);
+    if (!f) throw std::runtime_error("Cannot open file");
+    f << doc.serialize(true);
+}
+
 void makeDirs(const std::string &path)
 {
     for (size_t i = 1; i <= path.size(); ++i)
@@ -210,7 +257,6 @@ int run(const Options &opt)
     if (opt.str("optimizer") != "steepest_descent") throw std::runtime_error("Unknown optimizer type");
     // reference features outside the B200 hot path are refused rather than silently ignored
     if (opt.num("weight_noise_sigma") != 0) throw std::runtime_error("--weight_noise_sigma is not supported");
-    if (!opt.str("continue").empty()) throw std::runtime_error("--continue is not supported");
 
     Ctx ctx;
     if (bl_ctx_create(localRank, nullptr, &ctx.p)) throw std::runtime_error(std::string("bl_ctx_create: ") + bl_last_error(nullptr));
@@ -240,8 +286,9 @@ int run(const Options &opt)
     const int parallelSequences = (int)opt.num("parallel_sequences");
     const int truncSeq = (int)opt.num("truncate_seq");
 
-    if (chief) { std::printf("Reading network from '%s'... ", opt.str("network").c_str()); std::fflush(stdout); }
-    std::ifstream nf(opt.str("network").c_str(), std::ios::binary);
+    const std::string networkFile = opt.str("continue").empty() ? opt.str("network") : opt.str("continue");      // main.cpp:102
+    if (chief) { std::printf("Reading network from '%s'... ", networkFile.c_str()); std::fflush(stdout); }
+    std::ifstream nf(networkFile.c_str(), std::ios::binary);
     if (!nf) throw std::runtime_error("Cannot open file");
     std::stringstream nss; nss << nf.rdbuf();
     helpers::JsonDocument netDoc = helpers::parseJson(nss.str());
@@ -324,19 +371,27 @@ int run(const Options &opt)
         const bool haveVal = validationSet && !validationSet->empty(), haveTest = testSet && !testSet->empty();
         std::string prefix = opt.str("autosave_prefix");
         if (prefix.empty()) { const std::string &n = opt.str("network"); size_t pos = n.find_last_of('.'); prefix = (pos != std::string::npos && pos > 0) ? n.substr(0, pos) : n; }
-        bool finished = false;
+        std::string infoRows;
+        if (!opt.str("continue").empty()) {                                                    // main.cpp:198-204, 743-757
+            if (chief) { std::printf("Restoring state from '%s'... ", opt.str("continue").c_str()); std::fflush(stdout); }
+            if (!netDoc.HasMember("info_rows")) throw std::runtime_error("Missing value 'info_rows'");
+            infoRows = replaceAll(netDoc["info_rows"].GetString(), ";;;", "\n");
+            optimizer.importState(netDoc);
+            if (chief) { std::printf("done.\n\n"); std::fputs(infoRows.c_str(), stdout); }
+        }
+        bool finished = optimizer.finished();
         while (!finished) {
             const char *errFormat = classificationTask ? "%6.2lf%%%10.3lf |" : "%17.3lf |";
             const char *errSpace = "                  |";
-            printfRow(chief, " %5d | ", optimizer.currentEpoch() + 1);
+            infoRows += printfRow(chief, " %5d | ", optimizer.currentEpoch() + 1);
             const auto t0 = std::chrono::steady_clock::now();
             finished = optimizer.train();
             const double duration = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
-            printfRow(chief, "%8.1lf |", duration);
+            infoRows += printfRow(chief, "%8.1lf |", duration);
             auto cell = [&](bool due, double classErr, double err) {
-                if (!due) printfRow(chief, "%s", errSpace);
-                else if (classificationTask) printfRow(chief, errFormat, classErr * 100.0, err);
-                else printfRow(chief, errFormat, err);
+                if (!due) infoRows += printfRow(chief, "%s", errSpace);
+                else if (classificationTask) infoRows += printfRow(chief, errFormat, classErr * 100.0, err);
+                else infoRows += printfRow(chief, errFormat, err);
             };
             cell(true, optimizer.curTrainingClassError(), optimizer.curTrainingError());
             const bool valDue = haveVal && optimizer.currentEpoch() % validateEvery == 0;
@@ -344,13 +399,12 @@ int run(const Options &opt)
             cell(haveTest && optimizer.currentEpoch() % testEvery == 0, optimizer.curTestClassError(), optimizer.curTestError());
             if (valDue) {
                 if (optimizer.epochsSinceLowestValidationError() == 0) {
-                    printfRow(chief, "  yes   \n");
+                    infoRows += printfRow(chief, "  yes   \n");
                     if (chief && opt.flag("autosave_best") && !finished) saveNetwork(neuralNetwork, prefix + ".best.jsn");
-                } else printfRow(chief, "  no    \n");
-            } else printfRow(chief, "        \n");
-            if (chief && opt.flag("autosave") && !finished) {                               // weights only; optimizer state is not resumable here
-                char name[64]; std::snprintf(name, sizeof name, "epoch%03d.autosave", optimizer.currentEpoch());
-                saveNetwork(neuralNetwork, (opt.str("autosave_prefix").empty() ? prefix + "." : opt.str("autosave_prefix")) + name);
+                } else infoRows += printfRow(chief, "  no    \n");
+            } else infoRows += printfRow(chief, "        \n");
+            if (opt.flag("autosave")) {                                                        // main.cpp:275-277 (state is identical on every rank)
+                if (chief) saveState(neuralNetwork, optimizer, opt, infoRows);
             }
         }
         if (chief) {
@@ -434,6 +488,19 @@ int main(int argc, const char **argv)
         return 1;
     }
     if (opt.v.count("help")) { printHelp(); return 0; }
+    if (!opt.str("continue").empty()) {                                                 // options come from the autosave file
+        try {
+            std::ifstream f(opt.str("continue").c_str(), std::ios::binary);
+            if (!f) throw std::runtime_error("Cannot open file");
+            std::stringstream ss; ss << f.rdbuf();
+            const helpers::JsonDocument doc = helpers::parseJson(ss.str());
+            if (!doc.HasMember("configuration")) throw std::runtime_error("Missing string 'configuration'");
+            opt.restoreFrom(doc["configuration"].GetString());
+        } catch (const std::exception &e) {
+            std::fprintf(stderr, "Error while restoring configuration from autosave file: %s\n", e.what());
+            return 1;
+        }
+    }
     try {
         if (opt.flag("list_devices")) {
             std::printf("%d devices found\n", bl_device_count());

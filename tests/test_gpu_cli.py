@@ -187,6 +187,35 @@ def test_cli_context_windows_and_random_init(tmp_path):
     assert abs(float(np.std(wa[first][:4 * 10 * 117])) - 0.05) < 0.01                     # N(0, 0.05) input weights of the widened first layer
 
 
+def test_cli_autosave_and_continue(tmp_path):
+    """--autosave writes <prefix>_epochNNN.autosave (configuration, epoch table, network, optimizer state in the reference's JSON
+    fields); --continue resumes from it with the stored configuration and ends where the uninterrupted run ended (up to the
+    6 significant digits the file format keeps)."""
+    cfg, train, val, weights = _setup(tmp_path)
+    args = ["--network", "network.jsn", "--train", "true", "--train_file", "train.nc", "--val_file", "val.nc", "--stochastic", "true",
+            "--parallel_sequences", "10", "--learning_rate", "1e-3", "--momentum", "0.9", "--max_epochs", "3", "--autosave", "true",
+            "--autosave_prefix", "run", "--save_network", "full.jsn"]
+    out_a = _run(args, str(tmp_path))
+    saves = sorted(f for f in os.listdir(tmp_path) if f.endswith(".autosave"))
+    assert saves == ["run_epoch001.autosave", "run_epoch002.autosave", "run_epoch003.autosave"]
+    state = json.load(open(tmp_path / "run_epoch001.autosave"))
+    for key in ("configuration", "info_rows", "layers", "weights", "optimizer_finished", "optimizer_cur_epoch", "optimizer_lowest_validation_error",
+                "optimizer_best_weights", "steepest_descent_optimizer_weight_deltas"):
+        assert key in state, key
+    assert state["optimizer_cur_epoch"] == 1 and state["optimizer_finished"] is False and "max_epochs=3" in state["configuration"]
+    assert len(state["steepest_descent_optimizer_weight_deltas"]) == len(state["layers"])
+    os.rename(tmp_path / "full.jsn", tmp_path / "full_a.jsn")
+    out_b = _run(["--continue", "run_epoch001.autosave"], str(tmp_path))
+    assert "Restoring state from 'run_epoch001.autosave'... done." in out_b
+    rows_a, rows_b = _epoch_rows(out_a), _epoch_rows(out_b)
+    assert [r[0] for r in rows_b] == [1, 2, 3]                                      # the restored row of epoch 1, then the resumed epochs
+    for ra, rb in zip(rows_a, rows_b):
+        assert abs(ra[1] - rb[1]) <= 0.02 and abs(ra[2] - rb[2]) <= 0.002 and abs(ra[4] - rb[4]) <= 0.002
+    (_, wa), (_, wb) = _saved_weights(tmp_path / "full_a.jsn"), _saved_weights(tmp_path / "full.jsn")
+    for k in wa:
+        assert rel_err(wb[k], wa[k]) <= 1e-4
+
+
 def test_cli_data_parallel_two_processes(oracle, tmp_path):
     """Two processes x S=5 train like one process x S=10 (sum of gradients over the global fraction)."""
     import torch
