@@ -176,6 +176,10 @@ int bl_eval_scalar_fn(bl_ctx *ctx, int which, size_t n, const float *x, float *y
 int bl_sgd_update(bl_ctx *ctx, size_t n, float learningRate, float momentum, float *W, const float *dW, float *deltas);
 /* batch-mode gradient accumulation over fractions, thrust::transform(plus) of optimizers/Optimizer.cu:77-80: y += x */
 int bl_vector_add(bl_ctx *ctx, size_t n, const float *x, float *y);
+/* TrainableLayer::injectWeightNoise (layers/TrainableLayer.cu:188-209): w[e] += sigma * N(0,1).  The reference draws from a
+ * host mt19937 and copies the noise over; here element e of the call gets a counter-based draw from (seed, offset + e), so the
+ * same (seed, offset) gives the same noise on every rank.  The stream is NOT the reference's (documented in DESIGN.md). */
+int bl_add_gaussian_noise(bl_ctx *ctx, size_t n, float sigma, unsigned long long seed, unsigned long long offset, float *w);
 
 /* ------------------------------------------------------------------ data parallelism (new)
  * One communicator per process/GPU.  `unique_id` is the 128-byte ncclUniqueId produced by rank 0

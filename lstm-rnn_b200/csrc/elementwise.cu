@@ -227,6 +227,26 @@ __global__ void vector_add_kernel(size_t n, const float *__restrict__ x, float *
     for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (size_t)gridDim.x * blockDim.x) y[e] = __fadd_rn(y[e], x[e]);
 }
 
+// Counter-based Gaussian noise: element e of call `offset` draws from a hash of (seed, offset + e) -- reproducible and identical
+// on every data-parallel rank, with no generator state on the device.  Two 24-bit uniforms per element -> Box-Muller.
+__device__ __forceinline__ unsigned long long mix64(unsigned long long z)
+{
+    z += 0x9E3779B97F4A7C15ull;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+__global__ void add_gaussian_noise_kernel(size_t n, float sigma, unsigned long long seed, unsigned long long offset, float *__restrict__ w)
+{
+    for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (size_t)gridDim.x * blockDim.x) {
+        const unsigned long long r = mix64(mix64(seed) ^ (offset + e));
+        const float u1 = ((float)((r >> 40) & 0xFFFFFF) + 1.0f) * (1.0f / 16777216.0f);      // (0, 1]
+        const float u2 = (float)((r >> 8) & 0xFFFFFF) * (1.0f / 16777216.0f);                // [0, 1)
+        const float g = sqrtf(-2.0f * logf(u1)) * cospif(2.0f * u2);
+        w[e] = __fadd_rn(w[e], sigma * g);
+    }
+}
+
 __global__ void scalar_fn_kernel(int which, size_t n, const float *__restrict__ x, float *__restrict__ y)
 {
     for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (size_t)gridDim.x * blockDim.x) {
@@ -393,6 +413,15 @@ int bl_eval_scalar_fn(bl_ctx *ctx, int which, size_t n, const float *x, float *y
     if (which < 0 || which > 3) return fail(ctx, "bl_eval_scalar_fn: bad selector");
     if (!n) return 0;
     scalar_fn_kernel<<<ew_blocks(ctx, n, 256), 256, 0, ctx->stream>>>(which, n, x, y);
+    BL_LAUNCHED(ctx);
+    return 0;
+}
+
+int bl_add_gaussian_noise(bl_ctx *ctx, size_t n, float sigma, unsigned long long seed, unsigned long long offset, float *w)
+{
+    if (!n || sigma == 0.0f) return 0;
+    TimedRegion timed(ctx, 3);
+    add_gaussian_noise_kernel<<<ew_blocks(ctx, n, 256), 256, 0, ctx->stream>>>(n, sigma, seed, offset, w);
     BL_LAUNCHED(ctx);
     return 0;
 }

@@ -55,9 +55,35 @@ StepResult SteepestDescentOptimizer::trainFraction(const data_sets::DataSetFract
     StepResult r{0, 0, frac.validFrames()};
     if (frac.numSequences() == 0) {
         m_nn.contributeZeroGradients();           // empty shard of a data-parallel fraction
+        if (m_weightNoiseSigma > 0)                 // keep the noise counter in step with the ranks that do compute
+            for (const auto &layer : m_nn.layers()) {
+                layers::TrainableLayer *tl = dynamic_cast<layers::TrainableLayer *>(layer.get());
+                if (tl) m_weightNoiseCounter += tl->weights().size();
+            }
     } else {
         r = evalFraction(frac);
+        const bool noise = m_weightNoiseSigma > 0;
+        if (noise) {                                                              // Optimizer.cu:58-69
+            if (m_origWeights.empty())
+                for (const auto &layer : m_nn.layers()) {
+                    layers::TrainableLayer *tl = dynamic_cast<layers::TrainableLayer *>(layer.get());
+                    m_origWeights.emplace_back(new device::real_vector(ctx, tl ? tl->weights().size() : 0, false));
+                }
+            for (size_t i = 1; i + 1 < m_nn.layers().size(); ++i) {
+                layers::TrainableLayer *tl = dynamic_cast<layers::TrainableLayer *>(m_nn.layers()[i].get());
+                if (!tl) continue;
+                const size_t n = tl->weights().size();
+                check(ctx, bl_memcpy_d2d(ctx, m_origWeights[i]->data(), tl->weights().data(), n * sizeof(real_t)));
+                check(ctx, bl_add_gaussian_noise(ctx, n, m_weightNoiseSigma, m_weightNoiseSeed, m_weightNoiseCounter, tl->weights().data()));
+                m_weightNoiseCounter += n;
+            }
+        }
         m_nn.computeBackwardPass();
+        if (noise)                                                                // restore before the update (Optimizer.cu:84-86)
+            for (size_t i = 1; i + 1 < m_nn.layers().size(); ++i) {
+                layers::TrainableLayer *tl = dynamic_cast<layers::TrainableLayer *>(m_nn.layers()[i].get());
+                if (tl) check(ctx, bl_memcpy_d2d(ctx, tl->weights().data(), m_origWeights[i]->data(), tl->weights().size() * sizeof(real_t)));
+            }
     }
     m_nn.joinGradients();
     if (!m_hybridOnlineBatch) {

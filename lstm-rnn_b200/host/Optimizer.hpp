@@ -51,6 +51,10 @@ public:
     void exportState(helpers::JsonDocument &jsonDoc);
     void importState(const helpers::JsonDocument &jsonDoc);
 
+    // --weight_noise_sigma (Optimizer.cu:58-69, 84-86): Gaussian noise on every trainable layer's weights between the forward and
+    // the backward pass of a training fraction; the clean weights are restored before the update
+    void setWeightNoise(real_t sigma, unsigned seed) { m_weightNoiseSigma = sigma; m_weightNoiseSeed = seed; }
+
     real_t learningRate() const { return m_learningRate; }
     void setLearningRate(real_t lr) { m_learningRate = lr; }
     std::vector<std::vector<real_t>> weightDeltasToHost() const;
@@ -62,6 +66,8 @@ private:
     std::vector<std::unique_ptr<device::real_vector>> m_curWeightUpdates;   // batch mode accumulators
     std::vector<std::unique_ptr<device::real_vector>> m_weightDeltas;       // momentum state
     std::vector<std::unique_ptr<device::real_vector>> m_bestWeights;        // Optimizer.cu:106-127
+    std::vector<std::unique_ptr<device::real_vector>> m_origWeights;        // clean weights while the noise is injected
+    real_t m_weightNoiseSigma = 0; unsigned m_weightNoiseSeed = 0; unsigned long long m_weightNoiseCounter = 0;
     device::real_vector m_stats;                                            // {error, correct/4096, correct%4096} summed over ranks
 
     data_sets::DataSet *m_trainingSet = nullptr, *m_validationSet = nullptr, *m_testSet = nullptr;

@@ -255,9 +255,6 @@ int run(const Options &opt)
 
     if (!opt.flag("cuda")) throw std::runtime_error("--cuda false: this build has no CPU path");
     if (opt.str("optimizer") != "steepest_descent") throw std::runtime_error("Unknown optimizer type");
-    // reference features outside the B200 hot path are refused rather than silently ignored
-    if (opt.num("weight_noise_sigma") != 0) throw std::runtime_error("--weight_noise_sigma is not supported");
-
     Ctx ctx;
     if (bl_ctx_create(localRank, nullptr, &ctx.p)) throw std::runtime_error(std::string("bl_ctx_create: ") + bl_last_error(nullptr));
     const std::string gm = opt.str("gemm_mode");
@@ -357,6 +354,7 @@ int run(const Options &opt)
         optimizers::SteepestDescentOptimizer optimizer(neuralNetwork, (real_t)opt.num("learning_rate"), (real_t)opt.num("momentum"), stochastic);
         const int maxEpochs = (int)opt.num("max_epochs"), maxEpochsNoBest = (int)opt.num("max_epochs_no_best");
         const int validateEvery = (int)opt.num("validate_every"), testEvery = (int)opt.num("test_every");
+        optimizer.setWeightNoise((real_t)opt.num("weight_noise_sigma"), blob.seed);
         optimizer.setDataSets(trainingSet.get(), validationSet.get(), testSet.get(), maxEpochs, maxEpochsNoBest, validateEvery, testEvery);
         if (chief) {
             std::printf("Creating the optimizer... done.\nOptimizer type: Steepest descent with momentum\n");

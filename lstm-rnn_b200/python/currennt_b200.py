@@ -73,6 +73,7 @@ def libs():
         k.bl_ctx_timing_enable.argtypes = [vp, ci]
         k.bl_ctx_timing_read.argtypes = [vp, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_long)]
         k.bl_sgd_update.argtypes = [vp, ctypes.c_size_t, cf, cf, vp, vp, vp]
+        k.bl_add_gaussian_noise.argtypes = [vp, ctypes.c_size_t, cf, ctypes.c_ulonglong, ctypes.c_ulonglong, vp]
 
         h.cn_last_error.restype = cp
         h.cn_net_create.restype = vp

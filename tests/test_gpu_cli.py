@@ -170,12 +170,13 @@ def test_cli_rejects_what_it_does_not_implement(tmp_path):
 
 def test_cli_context_windows_and_random_init(tmp_path):
     """--input_left_context/--input_right_context widen the input layer to (l+r+1) x inputPattSize; without a weights section the
-    weights are drawn from --weights_dist with --random_seed, reproducibly."""
+    weights are drawn from --weights_dist with --random_seed, reproducibly -- as are --weight_noise_sigma and --input_noise_sigma."""
     cfg, train, val, weights = _setup(tmp_path)
     json.dump(json.loads(cfg["net"]), open(tmp_path / "plain.jsn", "w"))
     args = ["--network", "plain.jsn", "--train", "true", "--train_file", "train.nc", "--val_file", "val.nc", "--stochastic", "true",
             "--parallel_sequences", "8", "--learning_rate", "1e-4", "--max_epochs", "1", "--input_left_context", "1", "--input_right_context", "1",
-            "--output_time_lag", "1", "--weights_dist", "normal", "--weights_normal_sigma", "0.05", "--random_seed", "11"]
+            "--output_time_lag", "1", "--weights_dist", "normal", "--weights_normal_sigma", "0.05", "--random_seed", "11",
+            "--weight_noise_sigma", "0.01", "--input_noise_sigma", "0.1"]
     out1 = _run(args + ["--save_network", "a.jsn"], str(tmp_path))
     out2 = _run(args + ["--save_network", "b.jsn"], str(tmp_path))
     assert "(0) input [size: 117]" in out1

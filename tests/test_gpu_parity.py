@@ -332,6 +332,29 @@ def test_network_parity_with_tensor_core_gemms(oracle, gpu_ctx):
         gpu_ctx.set_gemm_backend(0)
 
 
+def test_weight_noise_kernel(gpu_ctx):
+    """bl_add_gaussian_noise (TrainableLayer::injectWeightNoise): N(0, sigma) per element, reproducible from (seed, offset), and a
+    call split in two continues the same stream."""
+    import ctypes
+    n, sigma = 1 << 20, 0.25
+    base = np.linspace(-1, 1, n).astype(np.float32)
+
+    def noise(seed, offset, count, start=0):
+        d = gpu_ctx.to_device(base[start:start + count])
+        gpu_ctx.check(gpu_ctx.k.bl_add_gaussian_noise(gpu_ctx.p, count, sigma, seed, offset, d))
+        out = gpu_ctx.to_host(d, (count,)) - base[start:start + count]
+        gpu_ctx.free(d)
+        return out
+
+    a, b, c = noise(7, 0, n), noise(7, 0, n), noise(8, 0, n)
+    assert np.array_equal(a, b) and not np.array_equal(a, c)
+    assert abs(a.mean()) < 4 * sigma / np.sqrt(n) and abs(a.std() - sigma) < 0.01 * sigma
+    assert abs(np.mean(np.abs(a) > 2 * sigma) - 0.0455) < 0.003                       # two-sigma tail of a normal distribution
+    half = n // 2
+    second = noise(7, half, n - half, start=half)
+    assert np.allclose(second, a[half:], atol=1e-6)                                   # same stream (fp32 add on a different base value)
+
+
 def test_fused_operand_split_is_bit_identical(oracle, gpu_ctx, monkeypatch):
     """The recurrent kernels write the TF32 hi/lo split of deltas and outputs while they store them; the separate split pass
     (BLSTM_NO_FUSED_SPLIT=1) must give bit-identical gradients -- both feed the same words to the same GEMMs."""
