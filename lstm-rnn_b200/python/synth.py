@@ -8,13 +8,15 @@ import numpy as np
 
 def network_json(input_size, hidden, output_size, output_type="softmax", post_type="multiclass_classification",
                  hidden_type="blstm", bias=1.0):
-    """hidden: list of sizes (int) or (type, size) pairs."""
+    """hidden: list of sizes (int) or (type, size) pairs.  The weightedsse / wf objectives are twice as wide as the output
+    layer (WeightedSsePostOutputLayer.cu:104, SseMaskPostOutputLayer.cu:104)."""
     layers = [{"size": int(input_size), "name": "input", "type": "input"}]
     for k, h in enumerate(hidden):
         t, sz = (hidden_type, h) if isinstance(h, int) else h
         layers.append({"size": int(sz), "name": "%s_%d" % (t, k), "bias": float(bias), "type": t})
     layers.append({"size": int(output_size), "name": "output", "bias": float(bias), "type": output_type})
-    layers.append({"size": int(output_size), "name": "postoutput", "type": post_type})
+    post_size = 2 * int(output_size) if post_type in ("weightedsse", "wf") else int(output_size)
+    layers.append({"size": post_size, "name": "postoutput", "type": post_type})
     return json.dumps({"layers": layers})
 
 

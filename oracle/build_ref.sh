@@ -11,7 +11,11 @@
 #      get<N>() -> rewrite `x.get<N>()` to `thrust::get<N>(x)` in the scratch copy.
 #   2. thrust::transform_reduce needs its own header -> -include thrust/transform_reduce.h
 #   3. Boost is absent -> oracle/boost_shim maps the 7 headers used onto the C++ standard library.
-#   4. Configuration.cpp / data_sets/DataSet.cpp need Boost.program_options / libnetcdf and are
+#   4. WeightedSsePostOutputLayer / SseMaskPostOutputLayer::calculateError reduce over bare counting iterators, which Thrust
+#      dispatches to its DEVICE backend even in the Cpu instantiation (host pointers on the GPU: it cannot run as written
+#      under --cuda false).  Those two translation units are compiled with THRUST_DEVICE_SYSTEM=CPP so that the same source
+#      runs its sequential host reduction; nothing else in them depends on the backend.
+#   5. Configuration.cpp / data_sets/DataSet.cpp need Boost.program_options / libnetcdf and are
 #      not on the hot path -> their few referenced symbols live in oracle/ref_harness/ref_harness.cu.
 set -euo pipefail
 
@@ -57,7 +61,10 @@ FLAGS=(-x cu -O3 -Xcompiler -O3,-fPIC -std=c++17 -arch=sm_100a -w
 pids=()
 for s in "${SRCS[@]}"; do
     o="$WORK/obj/$(echo "$s" | tr '/.' '__').o"
-    "$NVCC" "${FLAGS[@]}" -c "$WORK/src/$s" -o "$o" &
+    extra=()
+    case "$s" in layers/SseMaskPostOutputLayer.cu|layers/WeightedSsePostOutputLayer.cu)
+        extra=(-DTHRUST_DEVICE_SYSTEM=THRUST_DEVICE_SYSTEM_CPP) ;; esac
+    "$NVCC" "${FLAGS[@]}" "${extra[@]}" -c "$WORK/src/$s" -o "$o" &
     pids+=($!)
     # at most $(nproc) compilers at once
     while [ "$(jobs -rp | wc -l)" -ge "$(nproc)" ]; do sleep 0.2; done

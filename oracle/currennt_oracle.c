@@ -538,6 +538,112 @@ void orc_sse_backward(int O, int N, const char *patTypes, const real_t *targets,
         dY[i] = (patTypes[i / O] == PATTYPE_NONE) ? 0 : Y[i] - targets[i];
 }
 
+/* RmsePostOutputLayer::computeForwardPass (RmsePostOutputLayer.cu:39-67, 137-153): per-pattern RMSE into rmses[N]
+ * (0 for padded patterns) */
+void orc_rmse_forward(int O, int N, const char *patTypes, const real_t *targets, const real_t *Y, real_t *rmses)
+{
+    int n, i;
+    for (n = 0; n < N; ++n) {
+        real_t r = 0;
+        if (patTypes[n] != PATTYPE_NONE) {
+            real_t sum = 0;
+            for (i = 0; i < O; ++i) { real_t diff = Y[(size_t)n * O + i] - targets[(size_t)n * O + i]; sum = sum + diff * diff; }
+            r = sqrtf(sum / O);
+        }
+        rmses[n] = r;
+    }
+}
+
+/* RmsePostOutputLayer::calculateError (:126-134): thrust::reduce of the per-pattern RMSEs, pattern order */
+real_t orc_rmse_error(int N, const real_t *rmses)
+{
+    real_t total = 0; int n;
+    for (n = 0; n < N; ++n) total = total + rmses[n];
+    return total;
+}
+
+/* RmsePostOutputLayer::computeBackwardPass (:69-93, 155-170): error = rmse[pattern] * (y - t), every entry */
+void orc_rmse_backward(int O, int N, const real_t *rmses, const real_t *targets, const real_t *Y, real_t *dY)
+{
+    size_t i;
+    for (i = 0; i < (size_t)N * O; ++i) dY[i] = rmses[i / O] * (Y[i] - targets[i]);
+}
+
+/* WeightedSsePostOutputLayer (WeightedSsePostOutputLayer.cu:40-93, 121-164) and SseMaskPostOutputLayer ("wf",
+ * SseMaskPostOutputLayer.cu:40-93, 121-164): the post-output layer is twice as wide as the output layer, its targets
+ * hold (target, weight | filter input) pairs; O = size of the output layer */
+real_t orc_weightedsse_error(int O, int N, const char *patTypes, const real_t *targets, const real_t *Y)
+{
+    real_t sum = 0; size_t i;
+    for (i = 0; i < (size_t)N * O; ++i) {
+        real_t v = 0;
+        if (patTypes[i / O] != PATTYPE_NONE) { real_t diff = (Y[i] - targets[2 * i]) * targets[2 * i + 1]; v = diff * diff; }
+        sum = sum + v;
+    }
+    return 0.5f * sum;
+}
+
+void orc_weightedsse_backward(int O, int N, const char *patTypes, const real_t *targets, const real_t *Y, real_t *dY)
+{
+    size_t i;
+    for (i = 0; i < (size_t)N * O; ++i)
+        dY[i] = (patTypes[i / O] == PATTYPE_NONE) ? 0 : (Y[i] - targets[2 * i]) * targets[2 * i + 1];
+}
+
+real_t orc_ssemask_error(int O, int N, const char *patTypes, const real_t *targets, const real_t *Y)
+{
+    real_t sum = 0; size_t i;
+    for (i = 0; i < (size_t)N * O; ++i) {
+        real_t v = 0;
+        if (patTypes[i / O] != PATTYPE_NONE) { real_t diff = Y[i] * targets[2 * i + 1] - targets[2 * i]; v = diff * diff; }
+        sum = sum + v;
+    }
+    return 0.5f * sum;
+}
+
+void orc_ssemask_backward(int O, int N, const char *patTypes, const real_t *targets, const real_t *Y, real_t *dY)
+{
+    size_t i;
+    for (i = 0; i < (size_t)N * O; ++i)
+        dY[i] = (patTypes[i / O] == PATTYPE_NONE) ? 0 : (Y[i] * targets[2 * i + 1] - targets[2 * i]) * targets[2 * i + 1];
+}
+
+/* BinaryClassificationLayer::calculateError (BinaryClassificationLayer.cu:43-66, 165-181); targets are the target classes as reals */
+real_t orc_binary_error(int N, const char *patTypes, const real_t *targets, const real_t *Y)
+{
+    real_t sum = 0; int n;
+    for (n = 0; n < N; ++n) {
+        real_t v = 0;
+        if (patTypes[n] != PATTYPE_NONE) {
+            real_t act = (Y[n] > RL_MIN ? Y[n] : RL_MIN), p = (targets[n] > 0 ? act : 1 - act);
+            v = -logf(p);
+        }
+        sum = sum + v;
+    }
+    return sum;
+}
+
+/* BinaryClassificationLayer::countCorrectClassifications (:68-84, 132-147) */
+int orc_binary_count_correct(int N, const char *patTypes, const real_t *targets, const real_t *Y)
+{
+    int n, c = 0;
+    for (n = 0; n < N; ++n) c += (patTypes[n] != PATTYPE_NONE) && ((targets[n] > 0.5f) == (Y[n] > 0.5f));
+    return c;
+}
+
+/* BinaryClassificationLayer::computeBackwardPass (:86-112, 188-203): padded patterns keep whatever outputErrors held */
+void orc_binary_backward(int N, const char *patTypes, const real_t *targets, const real_t *Y, real_t *dY)
+{
+    int n;
+    for (n = 0; n < N; ++n) {
+        if (patTypes[n] == PATTYPE_NONE) continue;
+        {
+            real_t act = (Y[n] > RL_MIN ? Y[n] : RL_MIN), p = (targets[n] > 0 ? act : 1 - act);
+            dY[n] = (targets[n] > 0 ? -(1 / p) : (1 / p));
+        }
+    }
+}
+
 /* ------------------------------------------------------------------ optimizer step
  * UpdateWeightFn (optimizers/SteepestDescentOptimizer.cu:39-59): delta = momentum*delta - lr*grad; w += delta */
 void orc_sgd_update(long n, real_t learningRate, real_t momentum, real_t *weights, const real_t *weightUpdates,

@@ -27,6 +27,7 @@ c_int_p = ctypes.POINTER(ctypes.c_int)
 PATTYPE_NONE, PATTYPE_FIRST, PATTYPE_NORMAL, PATTYPE_LAST = 0, 1, 2, 3
 
 _ACT = {"feedforward_tanh": 0, "feedforward_logistic": 1, "feedforward_identity": 2, "softmax": 2}
+_PAIRED = {"weightedsse": "weightedsse", "wf": "ssemask"}     # objectives whose targets are (target, weight) pairs
 
 
 def build(ref=True):
@@ -95,6 +96,18 @@ def oracle_lib():
             getattr(L, "orc_%s_error" % name).restype = ctypes.c_float
             getattr(L, "orc_%s_error" % name).argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_char_p, c_float_p, c_float_p]
             getattr(L, "orc_%s_backward" % name).argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_char_p, c_float_p, c_float_p, c_float_p]
+        for name in ("weightedsse", "ssemask"):
+            getattr(L, "orc_%s_error" % name).restype = ctypes.c_float
+            getattr(L, "orc_%s_error" % name).argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_char_p, c_float_p, c_float_p]
+            getattr(L, "orc_%s_backward" % name).argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_char_p, c_float_p, c_float_p, c_float_p]
+        L.orc_rmse_forward.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_char_p, c_float_p, c_float_p, c_float_p]
+        L.orc_rmse_error.restype = ctypes.c_float
+        L.orc_rmse_error.argtypes = [ctypes.c_int, c_float_p]
+        L.orc_rmse_backward.argtypes = [ctypes.c_int, ctypes.c_int, c_float_p, c_float_p, c_float_p, c_float_p]
+        L.orc_binary_error.restype = ctypes.c_float
+        L.orc_binary_error.argtypes = [ctypes.c_int, ctypes.c_char_p, c_float_p, c_float_p]
+        L.orc_binary_count_correct.argtypes = [ctypes.c_int, ctypes.c_char_p, c_float_p, c_float_p]
+        L.orc_binary_backward.argtypes = [ctypes.c_int, ctypes.c_char_p, c_float_p, c_float_p, c_float_p]
         L.orc_sgd_update.argtypes = [ctypes.c_long, ctypes.c_float, ctypes.c_float, c_float_p, c_float_p, c_float_p]
         L.orc_matrix_product.argtypes = [c_float_p, ctypes.c_int, ctypes.c_int,
                                          c_float_p, ctypes.c_int, ctypes.c_int, ctypes.c_int,
@@ -196,6 +209,7 @@ class OracleNet:
                 h = self.L.orc_lstm_create(prev, size, int(t == "blstm"), S, maxT, float(ly["bias"]))
                 assert h, "odd blstm size"
             self.lstm.append(h)
+        self.rmses = np.zeros(n, np.float32)                           # RmsePostOutputLayer::m_rmses
         self.frac = None
 
     def __del__(self):
@@ -223,6 +237,8 @@ class OracleNet:
         self.outputs[0][:f.N] = f.inputs                              # InputLayer.cpp:49-60
         if f.targets is not None and self.outputs[-1] is not None:
             self.outputs[-1][:f.N] = f.targets                         # PostOutputLayer.cpp:77-78
+        if self.layers[-1]["type"] == "binary_classification":         # BinaryClassificationLayer.cu:155-162: classes copied as reals
+            self.outputs[-1][:f.N, 0] = f.target_classes
 
     def _pat(self):
         return self.frac.pat_types.ctypes.data_as(ctypes.c_char_p)
@@ -241,6 +257,9 @@ class OracleNet:
                                  _fp(self.outputs[i]))
                 if t == "softmax":
                     L.orc_softmax_forward(O, f.N, self._pat(), _fp(self.outputs[i]))
+            elif t == "rmse":                                          # the one post-output layer with a forward pass
+                self.rmses[:] = 0
+                L.orc_rmse_forward(ly["size"], f.N, self._pat(), _fp(self.outputs[i]), _fp(self.outputs[i - 1]), _fp(self.rmses))
 
     def calculate_error(self):
         f, L, t = self.frac, self.L, self.layers[-1]["type"]
@@ -251,10 +270,18 @@ class OracleNet:
             return float(L.orc_ce_error(O, f.N, self._pat(), _fp(self.outputs[-1]), _fp(y)))
         if t == "sse":
             return float(L.orc_sse_error(O, f.N, self._pat(), _fp(self.outputs[-1]), _fp(y)))
+        if t == "rmse":
+            return float(L.orc_rmse_error(f.N, _fp(self.rmses)))
+        if t in _PAIRED:                                               # post-output layer twice as wide as the output layer
+            return float(getattr(L, "orc_%s_error" % _PAIRED[t])(O // 2, f.N, self._pat(), _fp(self.outputs[-1]), _fp(y)))
+        if t == "binary_classification":
+            return float(L.orc_binary_error(f.N, self._pat(), _fp(self.outputs[-1]), _fp(y)))
         raise ValueError(t)
 
     def count_correct(self):
         f = self.frac
+        if self.layers[-1]["type"] == "binary_classification":
+            return int(self.L.orc_binary_count_correct(f.N, self._pat(), _fp(self.outputs[-1]), _fp(self.outputs[-2])))
         return int(self.L.orc_multiclass_count_correct(self.layers[-1]["size"], f.N,
                                                        f.target_classes.ctypes.data_as(c_int_p), _fp(self.outputs[-2])))
 
@@ -269,6 +296,13 @@ class OracleNet:
             if t == "multiclass_classification":
                 L.orc_multiclass_backward(O, f.N, f.target_classes.ctypes.data_as(c_int_p), _fp(self.outputs[i - 1]),
                                           _fp(self.output_errors[i - 1]))
+            elif t in _PAIRED:
+                getattr(L, "orc_%s_backward" % _PAIRED[t])(P, f.N, self._pat(), _fp(self.outputs[i]), _fp(self.outputs[i - 1]),
+                                                           _fp(self.output_errors[i - 1]))
+            elif t == "rmse":
+                L.orc_rmse_backward(O, f.N, _fp(self.rmses), _fp(self.outputs[i]), _fp(self.outputs[i - 1]), _fp(self.output_errors[i - 1]))
+            elif t == "binary_classification":
+                L.orc_binary_backward(f.N, self._pat(), _fp(self.outputs[i]), _fp(self.outputs[i - 1]), _fp(self.output_errors[i - 1]))
             elif t in ("ce", "sse"):
                 getattr(L, "orc_%s_backward" % t)(O, f.N, self._pat(), _fp(self.outputs[i]), _fp(self.outputs[i - 1]),
                                                   _fp(self.output_errors[i - 1]))

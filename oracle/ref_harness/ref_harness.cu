@@ -24,6 +24,7 @@
 #include "layers/LstmLayer.hpp"
 #include "layers/PostOutputLayer.hpp"
 #include "layers/MulticlassClassificationLayer.hpp"
+#include "layers/BinaryClassificationLayer.hpp"
 #include "helpers/JsonClasses.hpp"
 #include "rapidjson/document.h"
 
@@ -213,8 +214,11 @@ int cref_net_count_correct(void *p, int *n)
     CREF_TRY
     layers::MulticlassClassificationLayer<Cpu> *l =
         dynamic_cast<layers::MulticlassClassificationLayer<Cpu>*>(&((RefNet*)p)->net->postOutputLayer());
-    if (!l) throw std::runtime_error("post output layer is not multiclass_classification");
-    *n = l->countCorrectClassifications();
+    if (l) { *n = l->countCorrectClassifications(); return 0; }
+    layers::BinaryClassificationLayer<Cpu> *b =
+        dynamic_cast<layers::BinaryClassificationLayer<Cpu>*>(&((RefNet*)p)->net->postOutputLayer());
+    if (!b) throw std::runtime_error("post output layer is not a classification layer");
+    *n = b->countCorrectClassifications();
     return 0;
     CREF_CATCH(1)
 }

@@ -22,6 +22,11 @@ CASES = [
     ("sse_identity", synth.network_json(6, [8, 4], 6, "feedforward_identity", "sse"), 3, [5, 5, 7], 0, 6),
     ("ce_softmax", synth.network_json(6, [8], 5, "softmax", "ce"), 3, [3, 4, 6], 0, 5),
     ("equal_lengths", synth.network_json(4, [6], 3), 2, [5, 5], 3, 0),
+    ("rmse_identity", synth.network_json(6, [8], 4, "feedforward_identity", "rmse"), 3, [2, 5, 7], 0, 4),
+    ("weightedsse", synth.network_json(6, [8], 4, "feedforward_identity", "weightedsse"), 3, [3, 5, 6], 0, 8),
+    ("wf_mask", synth.network_json(6, [("lstm", 7)], 4, "feedforward_logistic", "wf"), 3, [3, 5, 6], 0, 8),
+    ("binary", synth.network_json(6, [8], 1, "feedforward_logistic", "binary_classification"), 4, [1, 4, 6, 6], 2, 0),
+    ("binary_short_last_fraction", synth.network_json(5, [6], 1, "feedforward_logistic", "binary_classification"), 4, [3, 5], 2, 0),
 ]
 
 
@@ -38,7 +43,7 @@ def test_restatement_matches_reference_bitwise(oracle, case):
     r, o = run_net(ref, weights, frac), run_net(orc, weights, frac)
     assert np.float32(r["error"]).tobytes() == np.float32(o["error"]).tobytes()
     layers = json.loads(net_json)["layers"]
-    if layers[-1]["type"] == "multiclass_classification":
+    if layers[-1]["type"] in ("multiclass_classification", "binary_classification"):
         assert ref.count_correct() == orc.count_correct()
     for i, ly in enumerate(layers[:-1]):
         assert np.array_equal(ref.get_outputs(i), orc.get_outputs(i)), (name, "outputs", i)
