@@ -165,6 +165,33 @@ int bl_sse_error(bl_ctx *ctx, int O, int N, const char *patTypes, const float *t
                  const float *Y, int ldy, float *d_error);
 int bl_sse_backward(bl_ctx *ctx, int O, int N, const char *patTypes, const float *targets, int ldt,
                     const float *Y, int ldy, float *dY, int lddy);
+/* WeightedSsePostOutputLayer (WeightedSsePostOutputLayer.cu:121-164) and SseMaskPostOutputLayer, type "wf"
+ * (SseMaskPostOutputLayer.cu:121-164).  O = size of the OUTPUT layer; a target row holds O (target, weight | filter
+ * input) pairs, so ldt >= 2*O.  weightedsse: 1/2 sum ((y-t)*w)^2, dY = (y-t)*w; wf: 1/2 sum (y*f-t)^2, dY = (y*f-t)*f */
+int bl_weightedsse_error(bl_ctx *ctx, int O, int N, const char *patTypes, const float *targets, int ldt,
+                         const float *Y, int ldy, float *d_error);
+int bl_weightedsse_backward(bl_ctx *ctx, int O, int N, const char *patTypes, const float *targets, int ldt,
+                            const float *Y, int ldy, float *dY, int lddy);
+int bl_ssemask_error(bl_ctx *ctx, int O, int N, const char *patTypes, const float *targets, int ldt,
+                     const float *Y, int ldy, float *d_error);
+int bl_ssemask_backward(bl_ctx *ctx, int O, int N, const char *patTypes, const float *targets, int ldt,
+                        const float *Y, int ldy, float *dY, int lddy);
+/* RmsePostOutputLayer: computeForwardPass fills rmses[N] = sqrt(mean_i (y-t)^2), 0 for padded patterns
+ * (RmsePostOutputLayer.cu:39-67, 137-153); calculateError sums them (:126-134); computeBackwardPass writes
+ * dY = rmses[pattern]*(y-t) for every entry (:75-93, 155-170) */
+int bl_rmse_forward(bl_ctx *ctx, int O, int N, const char *patTypes, const float *targets, int ldt,
+                    const float *Y, int ldy, float *rmses);
+int bl_rmse_error(bl_ctx *ctx, int N, const float *rmses, float *d_error);
+int bl_rmse_backward(bl_ctx *ctx, int O, int N, const float *rmses, const float *targets, int ldt,
+                     const float *Y, int ldy, float *dY, int lddy);
+/* BinaryClassificationLayer (one output per pattern, targets = the 0/1 target classes as reals, -1 for padding):
+ * calculateError = -sum log(t>0 ? a : 1-a), a = max(y, FLT_MIN), and countCorrectClassifications ((t>0.5)==(y>0.5)) in
+ * one pass (BinaryClassificationLayer.cu:43-84, 132-181); computeBackwardPass dY = -/+ 1/p, padded patterns untouched
+ * (:86-112, 188-203) */
+int bl_binary_error(bl_ctx *ctx, int N, const char *patTypes, const float *targets, int ldt, const float *Y, int ldy,
+                    float *d_error, int *d_correct);
+int bl_binary_backward(bl_ctx *ctx, int N, const char *patTypes, const float *targets, int ldt, const float *Y, int ldy,
+                       float *dY, int lddy);
 
 /* Elementwise evaluation of the scalar functions every kernel shares (parity tests pin them bit-for-bit against
  * the reference's functors): which = 0 Logistic::fn (Logistic.cuh:33-43), 1 Tanh::fn (Tanh.cuh:33-36),

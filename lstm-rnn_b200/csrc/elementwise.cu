@@ -157,8 +157,26 @@ __global__ void multiclass_bwd_kernel(int O, size_t total, const int *__restrict
     }
 }
 
-// CE / SSE objectives (CePostOutputLayer.cu:43-70, SsePostOutputLayer.cu:39-60): block partials
-template <bool CE>
+// Dense-target objectives, block partials.  KIND: SSE (SsePostOutputLayer.cu:39-60), CE (CePostOutputLayer.cu:43-70),
+// WSSE (WeightedSsePostOutputLayer.cu:40-65) and MASK ("wf", SseMaskPostOutputLayer.cu:40-65); the last two read
+// (target, weight | filter input) pairs from a target row twice as wide as the output row.
+enum { OBJ_SSE = 0, OBJ_CE = 1, OBJ_WSSE = 2, OBJ_MASK = 3 };
+
+template <int KIND>
+__device__ __forceinline__ float dense_error_term(const float *__restrict__ trow, int j, float y)
+{
+    if (KIND == OBJ_CE) {
+        const float t = trow[j], ft = fmaxf(BL_FLT_MIN, t), o = fmaxf(BL_FLT_MIN, y);
+        return __fmul_rn(t, logf(__fdiv_rn(ft, o)));
+    }
+    float diff;
+    if (KIND == OBJ_SSE)       diff = __fsub_rn(trow[j], y);
+    else if (KIND == OBJ_WSSE) diff = __fmul_rn(__fsub_rn(y, trow[2 * j]), trow[2 * j + 1]);
+    else                       diff = __fsub_rn(__fmul_rn(y, trow[2 * j + 1]), trow[2 * j]);
+    return __fmul_rn(diff, diff);
+}
+
+template <int KIND>
 __global__ void dense_error_kernel(int O, size_t total, const char *__restrict__ pat, const float *__restrict__ tg, int ldt,
                                    const float *__restrict__ Y, int ldy, float *__restrict__ part)
 {
@@ -167,14 +185,7 @@ __global__ void dense_error_kernel(int O, size_t total, const char *__restrict__
     for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
         const size_t n = e / O; const int j = (int)(e % O);
         if (pat[n] == BL_PATTYPE_NONE) continue;
-        const float t = tg[n * ldt + j], y = Y[n * ldy + j];
-        if (CE) {
-            const float ft = fmaxf(BL_FLT_MIN, t), o = fmaxf(BL_FLT_MIN, y);
-            acc += __fmul_rn(t, logf(__fdiv_rn(ft, o)));
-        } else {
-            const float diff = __fsub_rn(t, y);
-            acc += __fmul_rn(diff, diff);
-        }
+        acc += dense_error_term<KIND>(tg + n * ldt, j, Y[n * ldy + j]);
     }
     acc = warp_sum(acc);
     if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
@@ -195,8 +206,8 @@ __global__ void dense_error_finish_kernel(int nblocks, float scale, const float 
     }
 }
 
-// CePostOutputLayer.cu:72-98 / SsePostOutputLayer.cu:62-88
-template <bool CE>
+// CePostOutputLayer.cu:72-98 / SsePostOutputLayer.cu:62-88 / WeightedSsePostOutputLayer.cu:67-93 / SseMaskPostOutputLayer.cu:67-93
+template <int KIND>
 __global__ void dense_bwd_kernel(int O, size_t total, const char *__restrict__ pat, const float *__restrict__ tg, int ldt,
                                  const float *__restrict__ Y, int ldy, float *__restrict__ dY, int lddy)
 {
@@ -204,11 +215,98 @@ __global__ void dense_bwd_kernel(int O, size_t total, const char *__restrict__ p
         const size_t n = e / O; const int j = (int)(e % O);
         float v = 0.0f;
         if (pat[n] != BL_PATTYPE_NONE) {
-            const float t = tg[n * ldt + j], y = Y[n * ldy + j];
-            if (CE) { const float r = -__fdiv_rn(t, fmaxf(BL_FLT_MIN, y)); v = r < -100.0f ? -100.0f : (r > 100.0f ? 100.0f : r); }
-            else v = __fsub_rn(y, t);
+            const float *trow = tg + n * ldt; const float y = Y[n * ldy + j];
+            if (KIND == OBJ_CE) { const float r = -__fdiv_rn(trow[j], fmaxf(BL_FLT_MIN, y)); v = r < -100.0f ? -100.0f : (r > 100.0f ? 100.0f : r); }
+            else if (KIND == OBJ_SSE)  v = __fsub_rn(y, trow[j]);
+            else if (KIND == OBJ_WSSE) v = __fmul_rn(__fsub_rn(y, trow[2 * j]), trow[2 * j + 1]);
+            else { const float f = trow[2 * j + 1]; v = __fmul_rn(__fsub_rn(__fmul_rn(y, f), trow[2 * j]), f); }
         }
         dY[n * lddy + j] = v;
+    }
+}
+
+// RmsePostOutputLayer::computeForwardPass (RmsePostOutputLayer.cu:39-67, 137-153): one warp per pattern
+__global__ void rmse_fwd_kernel(int O, int N, const char *__restrict__ pat, const float *__restrict__ tg, int ldt,
+                                const float *__restrict__ Y, int ldy, float *__restrict__ rmses)
+{
+    const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+    for (int n = blockIdx.x * wpb + (threadIdx.x >> 5); n < N; n += gridDim.x * wpb) {
+        float r = 0.0f;
+        if (pat[n] != BL_PATTYPE_NONE) {
+            const float *y = Y + (size_t)n * ldy, *t = tg + (size_t)n * ldt;
+            float sum = 0.0f;
+            for (int i = lane; i < O; i += 32) { const float diff = __fsub_rn(y[i], t[i]); sum += __fmul_rn(diff, diff); }
+            sum = warp_sum(sum);
+            r = __fsqrt_rn(__fdiv_rn(sum, (float)O));
+        }
+        if (lane == 0) rmses[n] = r;
+    }
+}
+
+// RmsePostOutputLayer::calculateError (:126-134): sum of the per-pattern RMSEs, block partials
+__global__ void vector_sum_kernel(size_t n, const float *__restrict__ x, float *__restrict__ part)
+{
+    __shared__ float red[32];
+    float acc = 0.0f;
+    for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (size_t)gridDim.x * blockDim.x) acc += x[e];
+    acc = warp_sum(acc);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float s = 0.0f;
+        for (int i = 0; i < (int)(blockDim.x >> 5); ++i) s += red[i];
+        part[blockIdx.x] = s;
+    }
+}
+
+// RmsePostOutputLayer::computeBackwardPass (:75-93, 155-170): error = rmse[pattern] * (y - t) for every entry
+__global__ void rmse_bwd_kernel(int O, size_t total, const float *__restrict__ rmses, const float *__restrict__ tg, int ldt,
+                                const float *__restrict__ Y, int ldy, float *__restrict__ dY, int lddy)
+{
+    for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
+        const size_t n = e / O; const int j = (int)(e % O);
+        dY[n * lddy + j] = __fmul_rn(rmses[n], __fsub_rn(Y[n * ldy + j], tg[n * ldt + j]));
+    }
+}
+
+// BinaryClassificationLayer::calculateError + countCorrectClassifications (BinaryClassificationLayer.cu:43-84, 132-181):
+// one output per pattern; per-block partials of sum log(p) and of the correct count (finished by multiclass_error_finish_kernel,
+// which negates the sum).
+__global__ void binary_error_kernel(int N, const char *__restrict__ pat, const float *__restrict__ tg, int ldt,
+                                    const float *__restrict__ Y, int ldy, float *__restrict__ perr, int *__restrict__ pcor)
+{
+    __shared__ float serr[32]; __shared__ int scor[32];
+    float err = 0.0f; int cor = 0;
+    for (int n = blockIdx.x * blockDim.x + threadIdx.x; n < N; n += gridDim.x * blockDim.x) {
+        if (pat[n] == BL_PATTYPE_NONE) continue;
+        const float t = tg[(size_t)n * ldt], y = Y[(size_t)n * ldy];
+        const float act = fmaxf(y, BL_FLT_MIN);
+        const float p = t > 0.0f ? act : __fsub_rn(1.0f, act);
+        err += logf(p);
+        cor += ((t > 0.5f) == (y > 0.5f));
+    }
+    err = warp_sum(err);
+    for (int o = 16; o; o >>= 1) cor += __shfl_xor_sync(0xffffffffu, cor, o);
+    if ((threadIdx.x & 31) == 0) { serr[threadIdx.x >> 5] = err; scor[threadIdx.x >> 5] = cor; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float e = 0.0f; int c = 0;
+        for (int i = 0; i < (int)(blockDim.x >> 5); ++i) { e += serr[i]; c += scor[i]; }
+        perr[blockIdx.x] = e; pcor[blockIdx.x] = c;
+    }
+}
+
+// BinaryClassificationLayer::computeBackwardPass (:86-112, 188-203): padded patterns keep what outputErrors held
+__global__ void binary_bwd_kernel(int N, const char *__restrict__ pat, const float *__restrict__ tg, int ldt,
+                                  const float *__restrict__ Y, int ldy, float *__restrict__ dY, int lddy)
+{
+    for (int n = blockIdx.x * blockDim.x + threadIdx.x; n < N; n += gridDim.x * blockDim.x) {
+        if (pat[n] == BL_PATTYPE_NONE) continue;
+        const float t = tg[(size_t)n * ldt];
+        const float act = fmaxf(Y[(size_t)n * ldy], BL_FLT_MIN);
+        const float p = t > 0.0f ? act : __fsub_rn(1.0f, act);
+        const float r = __fdiv_rn(1.0f, p);
+        dY[(size_t)n * lddy] = t > 0.0f ? -r : r;
     }
 }
 
@@ -367,37 +465,105 @@ int bl_multiclass_backward(bl_ctx *ctx, int O, int N, const int *targetClasses, 
     return 0;
 }
 
-static int dense_error(bl_ctx *ctx, bool ce, int O, int N, const char *pat, const float *tg, int ldt, const float *Y, int ldy, float *d_error)
+} // extern "C" (templates cannot have C linkage)
+
+template <int KIND>
+static int dense_error(bl_ctx *ctx, int O, int N, const char *pat, const float *tg, int ldt, const float *Y, int ldy, float *d_error)
 {
-    if (ldt < O || ldy < O) return fail(ctx, "post-output error: leading dimension too small");
+    const int tw = (KIND == OBJ_WSSE || KIND == OBJ_MASK) ? 2 * O : O;
+    if (ldt < tw || ldy < O) return fail(ctx, "post-output error: leading dimension too small");
     const size_t total = (size_t)N * O;
     int blocks = ew_blocks(ctx, total, 256); if (blocks > 1024) blocks = 1024;
     BL_CHECK(ensure_scratch(ctx, (size_t)blocks * sizeof(float)));
     TimedRegion timed(ctx, 3);
-    if (ce) dense_error_kernel<true><<<blocks, 256, 0, ctx->stream>>>(O, total, pat, tg, ldt, Y, ldy, ctx->scratch);
-    else    dense_error_kernel<false><<<blocks, 256, 0, ctx->stream>>>(O, total, pat, tg, ldt, Y, ldy, ctx->scratch);
+    dense_error_kernel<KIND><<<blocks, 256, 0, ctx->stream>>>(O, total, pat, tg, ldt, Y, ldy, ctx->scratch);
     BL_LAUNCHED(ctx);
-    dense_error_finish_kernel<<<1, 32, 0, ctx->stream>>>(blocks, ce ? 1.0f : 0.5f, ctx->scratch, d_error);
+    dense_error_finish_kernel<<<1, 32, 0, ctx->stream>>>(blocks, KIND == OBJ_CE ? 1.0f : 0.5f, ctx->scratch, d_error);
     BL_LAUNCHED(ctx);
     return 0;
 }
 
-static int dense_backward(bl_ctx *ctx, bool ce, int O, int N, const char *pat, const float *tg, int ldt, const float *Y, int ldy, float *dY, int lddy)
+template <int KIND>
+static int dense_backward(bl_ctx *ctx, int O, int N, const char *pat, const float *tg, int ldt, const float *Y, int ldy, float *dY, int lddy)
 {
-    if (ldt < O || ldy < O || lddy < O) return fail(ctx, "post-output backward: leading dimension too small");
+    const int tw = (KIND == OBJ_WSSE || KIND == OBJ_MASK) ? 2 * O : O;
+    if (ldt < tw || ldy < O || lddy < O) return fail(ctx, "post-output backward: leading dimension too small");
     const size_t total = (size_t)N * O;
     const int blocks = ew_blocks(ctx, total, 256);
     TimedRegion timed(ctx, 3);
-    if (ce) dense_bwd_kernel<true><<<blocks, 256, 0, ctx->stream>>>(O, total, pat, tg, ldt, Y, ldy, dY, lddy);
-    else    dense_bwd_kernel<false><<<blocks, 256, 0, ctx->stream>>>(O, total, pat, tg, ldt, Y, ldy, dY, lddy);
+    dense_bwd_kernel<KIND><<<blocks, 256, 0, ctx->stream>>>(O, total, pat, tg, ldt, Y, ldy, dY, lddy);
     BL_LAUNCHED(ctx);
     return 0;
 }
 
-int bl_ce_error(bl_ctx *ctx, int O, int N, const char *p, const float *t, int ldt, const float *Y, int ldy, float *e) { return dense_error(ctx, true, O, N, p, t, ldt, Y, ldy, e); }
-int bl_sse_error(bl_ctx *ctx, int O, int N, const char *p, const float *t, int ldt, const float *Y, int ldy, float *e) { return dense_error(ctx, false, O, N, p, t, ldt, Y, ldy, e); }
-int bl_ce_backward(bl_ctx *ctx, int O, int N, const char *p, const float *t, int ldt, const float *Y, int ldy, float *dY, int lddy) { return dense_backward(ctx, true, O, N, p, t, ldt, Y, ldy, dY, lddy); }
-int bl_sse_backward(bl_ctx *ctx, int O, int N, const char *p, const float *t, int ldt, const float *Y, int ldy, float *dY, int lddy) { return dense_backward(ctx, false, O, N, p, t, ldt, Y, ldy, dY, lddy); }
+extern "C" {
+
+int bl_ce_error(bl_ctx *ctx, int O, int N, const char *p, const float *t, int ldt, const float *Y, int ldy, float *e) { return dense_error<OBJ_CE>(ctx, O, N, p, t, ldt, Y, ldy, e); }
+int bl_sse_error(bl_ctx *ctx, int O, int N, const char *p, const float *t, int ldt, const float *Y, int ldy, float *e) { return dense_error<OBJ_SSE>(ctx, O, N, p, t, ldt, Y, ldy, e); }
+int bl_weightedsse_error(bl_ctx *ctx, int O, int N, const char *p, const float *t, int ldt, const float *Y, int ldy, float *e) { return dense_error<OBJ_WSSE>(ctx, O, N, p, t, ldt, Y, ldy, e); }
+int bl_ssemask_error(bl_ctx *ctx, int O, int N, const char *p, const float *t, int ldt, const float *Y, int ldy, float *e) { return dense_error<OBJ_MASK>(ctx, O, N, p, t, ldt, Y, ldy, e); }
+int bl_ce_backward(bl_ctx *ctx, int O, int N, const char *p, const float *t, int ldt, const float *Y, int ldy, float *dY, int lddy) { return dense_backward<OBJ_CE>(ctx, O, N, p, t, ldt, Y, ldy, dY, lddy); }
+int bl_sse_backward(bl_ctx *ctx, int O, int N, const char *p, const float *t, int ldt, const float *Y, int ldy, float *dY, int lddy) { return dense_backward<OBJ_SSE>(ctx, O, N, p, t, ldt, Y, ldy, dY, lddy); }
+int bl_weightedsse_backward(bl_ctx *ctx, int O, int N, const char *p, const float *t, int ldt, const float *Y, int ldy, float *dY, int lddy) { return dense_backward<OBJ_WSSE>(ctx, O, N, p, t, ldt, Y, ldy, dY, lddy); }
+int bl_ssemask_backward(bl_ctx *ctx, int O, int N, const char *p, const float *t, int ldt, const float *Y, int ldy, float *dY, int lddy) { return dense_backward<OBJ_MASK>(ctx, O, N, p, t, ldt, Y, ldy, dY, lddy); }
+
+int bl_rmse_forward(bl_ctx *ctx, int O, int N, const char *patTypes, const float *targets, int ldt, const float *Y, int ldy, float *rmses)
+{
+    if (ldt < O || ldy < O) return fail(ctx, "bl_rmse_forward: leading dimension too small");
+    if (!N) return 0;
+    TimedRegion timed(ctx, 3);
+    rmse_fwd_kernel<<<ew_blocks(ctx, (size_t)N * 32, 256), 256, 0, ctx->stream>>>(O, N, patTypes, targets, ldt, Y, ldy, rmses);
+    BL_LAUNCHED(ctx);
+    return 0;
+}
+
+int bl_rmse_error(bl_ctx *ctx, int N, const float *rmses, float *d_error)
+{
+    int blocks = ew_blocks(ctx, (size_t)N, 256); if (blocks > 1024) blocks = 1024;
+    BL_CHECK(ensure_scratch(ctx, (size_t)blocks * sizeof(float)));
+    TimedRegion timed(ctx, 3);
+    vector_sum_kernel<<<blocks, 256, 0, ctx->stream>>>((size_t)N, rmses, ctx->scratch);
+    BL_LAUNCHED(ctx);
+    dense_error_finish_kernel<<<1, 32, 0, ctx->stream>>>(blocks, 1.0f, ctx->scratch, d_error);
+    BL_LAUNCHED(ctx);
+    return 0;
+}
+
+int bl_rmse_backward(bl_ctx *ctx, int O, int N, const float *rmses, const float *targets, int ldt, const float *Y, int ldy, float *dY, int lddy)
+{
+    if (ldt < O || ldy < O || lddy < O) return fail(ctx, "bl_rmse_backward: leading dimension too small");
+    const size_t total = (size_t)N * O;
+    if (!total) return 0;
+    TimedRegion timed(ctx, 3);
+    rmse_bwd_kernel<<<ew_blocks(ctx, total, 256), 256, 0, ctx->stream>>>(O, total, rmses, targets, ldt, Y, ldy, dY, lddy);
+    BL_LAUNCHED(ctx);
+    return 0;
+}
+
+int bl_binary_error(bl_ctx *ctx, int N, const char *patTypes, const float *targets, int ldt, const float *Y, int ldy,
+                    float *d_error, int *d_correct)
+{
+    if (ldt < 1 || ldy < 1) return fail(ctx, "bl_binary_error: leading dimension too small");
+    int blocks = ew_blocks(ctx, (size_t)N, 256); if (blocks > 1024) blocks = 1024;
+    BL_CHECK(ensure_scratch(ctx, (size_t)blocks * 2 * sizeof(float)));
+    float *perr = ctx->scratch; int *pcor = reinterpret_cast<int *>(ctx->scratch + blocks);
+    TimedRegion timed(ctx, 3);
+    binary_error_kernel<<<blocks, 256, 0, ctx->stream>>>(N, patTypes, targets, ldt, Y, ldy, perr, pcor);
+    BL_LAUNCHED(ctx);
+    multiclass_error_finish_kernel<<<1, 32, 0, ctx->stream>>>(blocks, perr, pcor, d_error, d_correct);
+    BL_LAUNCHED(ctx);
+    return 0;
+}
+
+int bl_binary_backward(bl_ctx *ctx, int N, const char *patTypes, const float *targets, int ldt, const float *Y, int ldy, float *dY, int lddy)
+{
+    if (ldt < 1 || ldy < 1 || lddy < 1) return fail(ctx, "bl_binary_backward: leading dimension too small");
+    if (!N) return 0;
+    TimedRegion timed(ctx, 3);
+    binary_bwd_kernel<<<ew_blocks(ctx, (size_t)N, 256), 256, 0, ctx->stream>>>(N, patTypes, targets, ldt, Y, ldy, dY, lddy);
+    BL_LAUNCHED(ctx);
+    return 0;
+}
 
 int bl_sgd_update(bl_ctx *ctx, size_t n, float lr, float mom, float *W, const float *dW, float *deltas)
 {

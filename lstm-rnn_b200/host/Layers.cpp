@@ -359,6 +359,122 @@ void CePostOutputLayer::computeBackwardPass()
                                 _actualOutputs().data(), preceding().ld(), _outputErrors().data(), preceding().ld()));
 }
 
+// ------------------------------------------------------------------ weightedsse / wf (layers/WeightedSsePostOutputLayer.cu:101-164,
+// layers/SseMaskPostOutputLayer.cu:101-164): size() is twice the output layer's size
+WeightedSsePostOutputLayer::WeightedSsePostOutputLayer(const helpers::JsonValue &layerChild, Layer &precedingLayer)
+    : PostOutputLayer(layerChild, precedingLayer, precedingLayer.size() * 2) {}
+const std::string &WeightedSsePostOutputLayer::type() const { static const std::string s("weightedsse"); return s; }
+
+real_t WeightedSsePostOutputLayer::calculateError()
+{
+    check(ctx(), bl_weightedsse_error(ctx(), size() / 2, curPatterns(), patTypes().data(), _targets().data(), ld(),
+                                      _actualOutputs().data(), preceding().ld(), m_devScalar.data()));
+    real_t e; m_devScalar.toHost(&e, 1);
+    return e;
+}
+
+void WeightedSsePostOutputLayer::computeBackwardPass()
+{
+    check(ctx(), bl_weightedsse_backward(ctx(), size() / 2, curPatterns(), patTypes().data(), _targets().data(), ld(),
+                                         _actualOutputs().data(), preceding().ld(), _outputErrors().data(), preceding().ld()));
+}
+
+SseMaskPostOutputLayer::SseMaskPostOutputLayer(const helpers::JsonValue &layerChild, Layer &precedingLayer)
+    : PostOutputLayer(layerChild, precedingLayer, precedingLayer.size() * 2) {}
+const std::string &SseMaskPostOutputLayer::type() const { static const std::string s("wf"); return s; }
+
+real_t SseMaskPostOutputLayer::calculateError()
+{
+    check(ctx(), bl_ssemask_error(ctx(), size() / 2, curPatterns(), patTypes().data(), _targets().data(), ld(),
+                                  _actualOutputs().data(), preceding().ld(), m_devScalar.data()));
+    real_t e; m_devScalar.toHost(&e, 1);
+    return e;
+}
+
+void SseMaskPostOutputLayer::computeBackwardPass()
+{
+    check(ctx(), bl_ssemask_backward(ctx(), size() / 2, curPatterns(), patTypes().data(), _targets().data(), ld(),
+                                     _actualOutputs().data(), preceding().ld(), _outputErrors().data(), preceding().ld()));
+}
+
+// ------------------------------------------------------------------ rmse (layers/RmsePostOutputLayer.cu:103-170)
+RmsePostOutputLayer::RmsePostOutputLayer(const helpers::JsonValue &layerChild, Layer &precedingLayer)
+    : PostOutputLayer(layerChild, precedingLayer, precedingLayer.size())
+    , m_rmses(precedingLayer.ctx(), (size_t)precedingLayer.parallelSequences() * precedingLayer.maxSeqLength(), true) {}
+const std::string &RmsePostOutputLayer::type() const { static const std::string s("rmse"); return s; }
+
+void RmsePostOutputLayer::computeForwardPass()
+{
+    check(ctx(), bl_rmse_forward(ctx(), size(), curPatterns(), patTypes().data(), _targets().data(), ld(),
+                                 _actualOutputs().data(), preceding().ld(), m_rmses.data()));
+}
+
+real_t RmsePostOutputLayer::calculateError()
+{
+    check(ctx(), bl_rmse_error(ctx(), curPatterns(), m_rmses.data(), m_devScalar.data()));
+    real_t e; m_devScalar.toHost(&e, 1);
+    return e;
+}
+
+void RmsePostOutputLayer::computeBackwardPass()
+{
+    check(ctx(), bl_rmse_backward(ctx(), size(), curPatterns(), m_rmses.data(), _targets().data(), ld(),
+                                  _actualOutputs().data(), preceding().ld(), _outputErrors().data(), preceding().ld()));
+}
+
+// ------------------------------------------------------------------ BinaryClassificationLayer (BinaryClassificationLayer.cu:119-203)
+BinaryClassificationLayer::BinaryClassificationLayer(const helpers::JsonValue &layerChild, Layer &precedingLayer)
+    : PostOutputLayer(layerChild, precedingLayer, precedingLayer.size())
+    , m_devCorrect(precedingLayer.ctx(), 1)
+    , m_evaluated(false), m_error(0), m_correct(0)
+{
+    if (this->size() != 1)
+        throw std::runtime_error("The binary classification post output layer cannot be used for an output layer size != 1");
+}
+
+const std::string &BinaryClassificationLayer::type() const { static const std::string s("binary_classification"); return s; }
+
+void BinaryClassificationLayer::loadSequences(const data_sets::DataSetFraction &fraction)
+{
+    PostOutputLayer::loadSequences(fraction);
+    if (fraction.targetClasses().size() < (size_t)curPatterns())
+        throw std::runtime_error("The data fraction carries no target classes");
+    // the target classes are the real target values 0/1 (-1 for padded patterns), :155-162
+    m_hostTargets.resize((size_t)curPatterns());
+    for (size_t n = 0; n < m_hostTargets.size(); ++n) m_hostTargets[n] = (real_t)fraction.targetClasses()[n];
+    _targets().fromHost(m_hostTargets.data(), m_hostTargets.size());           // ld() == size() == 1
+    m_evaluated = false;
+}
+
+void BinaryClassificationLayer::evaluate()
+{
+    check(ctx(), bl_binary_error(ctx(), curPatterns(), patTypes().data(), _targets().data(), ld(), _actualOutputs().data(),
+                                 preceding().ld(), m_devScalar.data(), m_devCorrect.data()));
+    check(ctx(), bl_memcpy_d2h(ctx(), &m_error, m_devScalar.data(), sizeof(real_t)));
+    check(ctx(), bl_memcpy_d2h(ctx(), &m_correct, m_devCorrect.data(), sizeof(int)));
+    check(ctx(), bl_sync(ctx()));
+    m_evaluated = true;
+}
+
+real_t BinaryClassificationLayer::calculateError()
+{
+    evaluate();
+    return m_error;
+}
+
+int BinaryClassificationLayer::countCorrectClassifications()
+{
+    if (!m_evaluated) evaluate();
+    m_evaluated = false;
+    return m_correct;
+}
+
+void BinaryClassificationLayer::computeBackwardPass()
+{
+    check(ctx(), bl_binary_backward(ctx(), curPatterns(), patTypes().data(), _targets().data(), ld(), _actualOutputs().data(),
+                                    preceding().ld(), _outputErrors().data(), preceding().ld()));
+}
+
 // ------------------------------------------------------------------ MulticlassClassificationLayer (MulticlassClassificationLayer.cu:141-240)
 MulticlassClassificationLayer::MulticlassClassificationLayer(const helpers::JsonValue &layerChild, Layer &precedingLayer)
     : PostOutputLayer(layerChild, precedingLayer, precedingLayer.size(), false)

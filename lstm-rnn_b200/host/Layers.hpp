@@ -182,6 +182,56 @@ public:
     virtual void computeBackwardPass();
 };
 
+// weightedsse / wf: twice as wide as the output layer, targets are (target, weight | filter input) pairs
+// (layers/WeightedSsePostOutputLayer.cu, layers/SseMaskPostOutputLayer.cu)
+class WeightedSsePostOutputLayer : public PostOutputLayer {
+public:
+    WeightedSsePostOutputLayer(const helpers::JsonValue &layerChild, Layer &precedingLayer);
+    virtual const std::string &type() const;
+    virtual real_t calculateError();
+    virtual void computeForwardPass() {}
+    virtual void computeBackwardPass();
+};
+
+class SseMaskPostOutputLayer : public PostOutputLayer {
+public:
+    SseMaskPostOutputLayer(const helpers::JsonValue &layerChild, Layer &precedingLayer);
+    virtual const std::string &type() const;
+    virtual real_t calculateError();
+    virtual void computeForwardPass() {}
+    virtual void computeBackwardPass();
+};
+
+// layers/RmsePostOutputLayer.cu: the per-pattern RMSEs are computed in the forward pass and reused by both other calls
+class RmsePostOutputLayer : public PostOutputLayer {
+public:
+    RmsePostOutputLayer(const helpers::JsonValue &layerChild, Layer &precedingLayer);
+    virtual const std::string &type() const;
+    virtual real_t calculateError();
+    virtual void computeForwardPass();
+    virtual void computeBackwardPass();
+private:
+    real_vector m_rmses;
+};
+
+// layers/BinaryClassificationLayer.cu: one logistic output, targets = the target classes copied as reals
+class BinaryClassificationLayer : public PostOutputLayer {
+public:
+    BinaryClassificationLayer(const helpers::JsonValue &layerChild, Layer &precedingLayer);
+    virtual const std::string &type() const;
+    virtual void loadSequences(const data_sets::DataSetFraction &fraction);
+    virtual real_t calculateError();
+    int countCorrectClassifications();
+    virtual void computeForwardPass() {}
+    virtual void computeBackwardPass();
+private:
+    void evaluate();
+    device::Vector<int> m_devCorrect;
+    std::vector<real_t> m_hostTargets;
+    bool m_evaluated;
+    real_t m_error; int m_correct;
+};
+
 class MulticlassClassificationLayer : public PostOutputLayer {
 public:
     MulticlassClassificationLayer(const helpers::JsonValue &layerChild, Layer &precedingLayer);

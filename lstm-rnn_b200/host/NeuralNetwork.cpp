@@ -30,9 +30,14 @@ layers::Layer *LayerFactory::createLayer(bl_ctx *ctx, const std::string &layerTy
         return new CePostOutputLayer(layerChild, *precedingLayer);
     if (layerType == "multiclass_classification")
         return new MulticlassClassificationLayer(layerChild, *precedingLayer);
-    // the reference's factory also knows these objectives (LayerFactory.cu:66-81); they are outside the hot path
-    if (layerType == "weightedsse" || layerType == "rmse" || layerType == "wf" || layerType == "binary_classification")
-        throw std::runtime_error("Layer type '" + layerType + "' is not part of the B200 hot path (SURVEY.md section 2, row 16)");
+    if (layerType == "weightedsse")
+        return new WeightedSsePostOutputLayer(layerChild, *precedingLayer);
+    if (layerType == "rmse")
+        return new RmsePostOutputLayer(layerChild, *precedingLayer);
+    if (layerType == "wf")          // "sse_mask" never reaches the reference's constructor either (LayerFactory.cu:66, 79)
+        return new SseMaskPostOutputLayer(layerChild, *precedingLayer);
+    if (layerType == "binary_classification")
+        return new BinaryClassificationLayer(layerChild, *precedingLayer);
     throw std::runtime_error(std::string("Unknown layer type '") + layerType + "'");
 }
 

@@ -46,6 +46,8 @@ StepResult SteepestDescentOptimizer::evalFraction(const data_sets::DataSetFracti
     r.error = m_nn.calculateError();
     layers::MulticlassClassificationLayer *mc = dynamic_cast<layers::MulticlassClassificationLayer *>(&m_nn.postOutputLayer());
     if (mc) r.correct = mc->countCorrectClassifications();
+    layers::BinaryClassificationLayer *bc = dynamic_cast<layers::BinaryClassificationLayer *>(&m_nn.postOutputLayer());
+    if (bc) r.correct = bc->countCorrectClassifications();                                       // Optimizer.cu:52-55
     return r;
 }
 

@@ -147,8 +147,10 @@ int cn_net_count_correct(cn_net *net, int *c)
 {
     CN_TRY
     layers::MulticlassClassificationLayer *l = dynamic_cast<layers::MulticlassClassificationLayer *>(&net->net->postOutputLayer());
-    if (!l) throw std::runtime_error("post output layer is not multiclass_classification");
-    *c = l->countCorrectClassifications();
+    if (l) { *c = l->countCorrectClassifications(); return 0; }
+    layers::BinaryClassificationLayer *b = dynamic_cast<layers::BinaryClassificationLayer *>(&net->net->postOutputLayer());
+    if (!b) throw std::runtime_error("post output layer is not a classification layer");
+    *c = b->countCorrectClassifications();
     return 0;
     CN_CATCH(1)
 }

@@ -347,7 +347,8 @@ int run(const Options &opt)
         }
         std::printf("Total weights: %d\n\n\n", [&] { int n = 0; for (const auto &l : neuralNetwork.layers()) { auto *tl = dynamic_cast<const layers::TrainableLayer *>(l.get()); if (tl) n += (int)tl->weights().size(); } return n; }());
     }
-    const bool classificationTask = dynamic_cast<layers::MulticlassClassificationLayer *>(&neuralNetwork.postOutputLayer()) != nullptr;
+    const bool classificationTask = dynamic_cast<layers::MulticlassClassificationLayer *>(&neuralNetwork.postOutputLayer()) != nullptr
+                                 || dynamic_cast<layers::BinaryClassificationLayer *>(&neuralNetwork.postOutputLayer()) != nullptr;
 
     if (training) {
         const bool stochastic = opt.flag("stochastic") || opt.flag("hybrid_online_batch");

@@ -100,6 +100,15 @@ NET_CASES = [
     ("odd_sizes_wide", synth.network_json(23, [62, 30], 19), 7, [9, 11, 14, 14, 15, 15, 16], 19, 0),
     ("many_sequences", synth.network_json(10, [20], 8), 37, list(range(4, 41)), 8, 0),
     ("mid_blstm_250", synth.network_json(41, [250], 33), 12, [5, 7, 9, 9, 10, 12, 12, 12, 13, 13, 14, 14], 33, 0),
+    # the remaining objectives of LayerFactory.cu:66-81
+    ("rmse_identity", synth.network_json(6, [8], 4, "feedforward_identity", "rmse"), 3, [2, 5, 7], 0, 4),
+    ("rmse_wide", synth.network_json(12, [20], 37, "feedforward_identity", "rmse"), 6, [4, 6, 9, 9, 10, 11], 0, 37),
+    ("weightedsse", synth.network_json(6, [8], 4, "feedforward_identity", "weightedsse"), 3, [3, 5, 6], 0, 8),
+    ("weightedsse_odd", synth.network_json(9, [12], 7, "feedforward_tanh", "weightedsse"), 5, [1, 4, 6, 8, 8], 0, 14),
+    ("wf_mask", synth.network_json(6, [("lstm", 7)], 4, "feedforward_logistic", "wf"), 3, [3, 5, 6], 0, 8),
+    ("binary", synth.network_json(6, [8], 1, "feedforward_logistic", "binary_classification"), 4, [1, 4, 6, 6], 2, 0),
+    ("binary_short_last_fraction", synth.network_json(5, [6], 1, "feedforward_logistic", "binary_classification"), 4, [3, 5], 2, 0),
+    ("binary_many", synth.network_json(8, [10], 1, "feedforward_logistic", "binary_classification"), 33, list(range(3, 36)), 2, 0),
 ]
 
 
@@ -114,7 +123,7 @@ def check_net(oracle, gpu_ctx, net_json, S, lengths, classes, tsize, seed=11, ce
     o, g = run_net(orc, weights, frac), run_net(gpu, weights, frac)
     assert abs(g["error"] - o["error"]) <= tol * abs(o["error"]) + 1e-10
     layers = json.loads(net_json)["layers"]
-    if layers[-1]["type"] == "multiclass_classification":
+    if layers[-1]["type"] in ("multiclass_classification", "binary_classification"):
         assert gpu.count_correct() == orc.count_correct()
     worst = 0.0
     valid = frac.pat_types != 0
