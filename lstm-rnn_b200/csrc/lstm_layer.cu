@@ -27,6 +27,7 @@ struct bl_lstm_plan {
     float bias;
     bl::RecGeom gf, gb;
     bool reg_f, reg_b;       // register-resident persistent kernels (lstm_recurrent_reg.cu) vs shared-memory ones
+    bool tm_f;               // forward: tensor-memory-resident weights + tcgen05 step GEMM (lstm_recurrent_tmem.cu)
     float *acts, *deltas, *cst, *cerr, *hx, *dx, *gpart;
     long long *trace;
     float *tcbuf;            // prepared tensor-core operands (hi then lo of each): X, Win (forward); deltas, Y, Win re-blocked (backward)
@@ -127,13 +128,16 @@ int bl_lstm_plan_create(bl_ctx *ctx, int P, int L, int bidirectional, int S, int
 
     const int cap = ctx->smem_optin - 2048;      // room for the kernels' static shared memory (exp table) and the driver's reserve
     // tuning overrides (tools/sweep_geometry.py): sequence groups / sub-CTAs / threads of either kernel, and the kernel family
-    // (BLSTM_REC_V=2 forces the shared-memory-resident kernels; default: register-resident weights whenever the slice fits)
+    // (BLSTM_REC_V=2 forces the shared-memory-resident kernels, BLSTM_REC_V=3 selects the tensor-memory-resident forward kernel
+    // where it fits; default: register-resident weights whenever the slice fits)
     const char *ef = getenv("BLSTM_FWD_G"), *eb = getenv("BLSTM_BWD_G"), *nf = getenv("BLSTM_FWD_NSUB"), *nb = getenv("BLSTM_BWD_NSUB"),
                *tf = getenv("BLSTM_FWD_NT"), *tb = getenv("BLSTM_BWD_NT"), *ev = getenv("BLSTM_REC_V");
-    const bool want_reg = !(ev && atoi(ev) == 2);
-    pl->reg_f = want_reg && bl::choose_geometry_reg(false, pl->H, S, pl->ndir, ctx->num_sms, cap, ef ? atoi(ef) : 0, &pl->gf);
+    const int family = ev ? atoi(ev) : 0;
+    const bool want_reg = family != 2;
+    pl->tm_f = family == 3 && bl::choose_geometry_tmem(pl->H, S, pl->ndir, ctx->num_sms, cap, ef ? atoi(ef) : 0, &pl->gf);
+    pl->reg_f = !pl->tm_f && want_reg && bl::choose_geometry_reg(false, pl->H, S, pl->ndir, ctx->num_sms, cap, ef ? atoi(ef) : 0, &pl->gf);
     pl->reg_b = want_reg && bl::choose_geometry_reg(true, pl->H, S, pl->ndir, ctx->num_sms, cap, eb ? atoi(eb) : 0, &pl->gb);
-    if ((!pl->reg_f && !bl::choose_geometry(false, pl->H, S, pl->ndir, ctx->num_sms, cap, ef ? atoi(ef) : 0, nf ? atoi(nf) : 0, tf ? atoi(tf) : 0, &pl->gf)) ||
+    if ((!pl->tm_f && !pl->reg_f && !bl::choose_geometry(false, pl->H, S, pl->ndir, ctx->num_sms, cap, ef ? atoi(ef) : 0, nf ? atoi(nf) : 0, tf ? atoi(tf) : 0, &pl->gf)) ||
         (!pl->reg_b && !bl::choose_geometry(true, pl->H, S, pl->ndir, ctx->num_sms, cap, eb ? atoi(eb) : 0, nb ? atoi(nb) : 0, tb ? atoi(tb) : 0, &pl->gb))) {
         delete pl;
         return bl::fail(ctx, "bl_lstm_plan_create: no persistent-kernel geometry fits (H=%d S=%d): recurrent weights do not fit on chip",
@@ -179,7 +183,9 @@ void bl_lstm_plan_destroy(bl_lstm_plan *pl)
 int bl_lstm_plan_info(const bl_lstm_plan *pl, int *o)
 {
     // smem is a multiple of 4: the low two bits carry nsub (1, 2, 4 -> 1, 2, 0), or 3 for the register-resident kernels
-    o[0] = pl->gf.G; o[1] = pl->gf.C; o[2] = pl->gf.CL; o[3] = (int)pl->gf.smem + (pl->reg_f ? 3 : pl->gf.nsub);
+    // (the tensor-memory forward kernel reports its smem rounded up to 16 with 11 in the low four bits)
+    o[0] = pl->gf.G; o[1] = pl->gf.C; o[2] = pl->gf.CL;
+    o[3] = pl->tm_f ? (int)((pl->gf.smem + 15) & ~(size_t)15) + 11 : (int)pl->gf.smem + (pl->reg_f ? 3 : pl->gf.nsub);
     o[4] = pl->gb.G; o[5] = pl->gb.C; o[6] = pl->gb.CL; o[7] = (int)pl->gb.smem + (pl->reg_b ? 3 : pl->gb.nsub);
     return 0;
 }
@@ -241,12 +247,12 @@ int bl_lstm_forward(bl_lstm_plan *pl, const float *W, const float *X, int ldx, c
     // the tensor-core backward pass wants the TF32 split of Y: the register-resident kernel writes it while it stores Y
     p.ys_hi = p.ys_lo = nullptr; p.ld_ys = 0;
     pl->ysplit_T = 0;
-    if (pl->reg_f && bl::tc_wanted(ctx, P, 4 * L, N) && getenv("BLSTM_NO_FUSED_SPLIT") == nullptr) {
+    if ((pl->reg_f || pl->tm_f) && bl::tc_wanted(ctx, P, 4 * L, N) && getenv("BLSTM_NO_FUSED_SPLIT") == nullptr) {
         BL_CHECK(plan_tc_buffers(pl));
         p.ys_hi = pl->tc_Y; p.ys_lo = pl->tc_Y + pl->tc_eY; p.ld_ys = (int)bl::tc_operand_ld(pl->ndir * ((H + 3) & ~3));
         pl->ysplit_T = T;
     }
-    BL_CHECK(pl->reg_f ? bl::launch_lstm_fwd_reg(ctx, p) : bl::launch_lstm_fwd(ctx, p));
+    BL_CHECK(pl->tm_f ? bl::launch_lstm_fwd_tmem(ctx, p) : pl->reg_f ? bl::launch_lstm_fwd_reg(ctx, p) : bl::launch_lstm_fwd(ctx, p));
     pl->lastT = T;
     return 0;
 }

@@ -385,6 +385,10 @@ class Net:
         self._chk(self.h.cn_lstm_plan_info(self.p, i, out))
         d = dict(zip(("fwd_G", "fwd_C", "fwd_CL", "fwd_smem", "bwd_G", "bwd_C", "bwd_CL", "bwd_smem"), [int(x) for x in out]))
         for k in ("fwd", "bwd"):                      # the low two bits of the (4-byte aligned) smem size carry nsub (1, 2 or 4 -> 1, 2, 0)
+            if (d[k + "_smem"] & 15) == 11:            # tensor-memory-resident forward kernel
+                d[k + "_kernel"], d[k + "_nsub"] = "tmem", 1
+                d[k + "_smem"] &= ~15
+                continue
             low = d[k + "_smem"] & 3
             d[k + "_kernel"] = "registers" if low == 3 else "smem"
             d[k + "_nsub"] = 1 if low == 3 else (low or 4)

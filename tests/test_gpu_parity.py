@@ -120,9 +120,13 @@ def check_net(oracle, gpu_ctx, net_json, S, lengths, classes, tsize, seed=11, ce
         frac.targets[:] = t / t.sum(1, keepdims=True)
     maxT = max(lengths) + 2
     orc, gpu = oracle.OracleNet(net_json, S, maxT), cb.Net(gpu_ctx, net_json, S, maxT)
+    return compare_nets(orc, gpu, weights, frac, json.loads(net_json)["layers"], S, tol)
+
+
+def compare_nets(orc, gpu, weights, frac, layers, S, tol=STRICT_TOL):
+    """One fraction through both networks; every observable tensor within `tol` (max|a-b|/max|b|), counts exact."""
     o, g = run_net(orc, weights, frac), run_net(gpu, weights, frac)
     assert abs(g["error"] - o["error"]) <= tol * abs(o["error"]) + 1e-10
-    layers = json.loads(net_json)["layers"]
     if layers[-1]["type"] in ("multiclass_classification", "binary_classification"):
         assert gpu.count_correct() == orc.count_correct()
     worst = 0.0
@@ -173,18 +177,55 @@ def test_sequence_group_geometries(oracle, gpu_ctx, G, monkeypatch):
     print("G=%d worst rel err %.2e" % (G, worst))
 
 
-@pytest.mark.parametrize("family", ["registers", "smem"])
+@pytest.mark.parametrize("family", ["registers", "smem", "tmem"])
 def test_both_recurrent_kernel_families(oracle, gpu_ctx, family, monkeypatch):
-    """Register-resident (default) and shared-memory-resident (BLSTM_REC_V=2, the fallback for slices that do not fit the
-    register file) kernels implement the same step protocol and must both hold the parity bar."""
+    """Register-resident (default), shared-memory-resident (BLSTM_REC_V=2, the fallback for slices that do not fit the
+    register file) and tensor-memory-resident (BLSTM_REC_V=3: forward step GEMM on tcgen05 with the weights in TMEM) kernels
+    implement the same step protocol and must all hold the parity bar."""
     import currennt_b200 as cb
     if family == "smem":
         monkeypatch.setenv("BLSTM_REC_V", "2")
+    if family == "tmem":
+        monkeypatch.setenv("BLSTM_REC_V", "3")
     net_json = synth.network_json(13, [48, ("lstm", 27)], 11)
     info = cb.Net(gpu_ctx, net_json, 6, 16).plan_info(1)
-    assert info["fwd_kernel"] == family and info["bwd_kernel"] == family, info
+    assert info["fwd_kernel"] == family and info["bwd_kernel"] == ("registers" if family == "tmem" else family), info
     worst = check_net(oracle, gpu_ctx, net_json, 6, [1, 4, 9, 9, 12, 14], 11, 0, seed=21)
     print(family, "worst rel err %.2e" % worst)
+
+
+TMEM_CASES = [
+    # name, net, S, lengths, classes, forced sequence groups (0 = cost model)
+    ("blstm_ragged", synth.network_json(7, [6], 5), 4, [3, 5, 5, 8], 5, 0),
+    ("one_group_n16", synth.network_json(11, [34, ("lstm", 21)], 9), 9, [2, 5, 6, 6, 8, 11, 11, 12, 13], 9, 1),
+    ("one_group_n32", synth.network_json(10, [20], 8), 29, list(range(4, 33)), 8, 1),
+    ("cells_span_slices", synth.network_json(9, [("lstm", 70), 44], 6), 5, [1, 4, 7, 7, 9], 6, 2),
+    ("h250_padded_k", synth.network_json(41, [500], 33), 12, [5, 7, 9, 9, 10, 12, 12, 12, 13, 13, 14, 14], 33, 0),
+    ("h256_full_k", synth.network_json(17, [("lstm", 256)], 9), 7, [3, 4, 6, 6, 7, 9, 9], 9, 0),
+]
+
+
+@pytest.mark.parametrize("case", TMEM_CASES, ids=[c[0] for c in TMEM_CASES])
+def test_tensor_memory_forward_kernel(oracle, gpu_ctx, case, monkeypatch):
+    """lstm_fwd_tmem_kernel (BLSTM_REC_V=3) against the oracle at the strict bar: N=16 and N=32 tiles, slices with fewer than 32
+    cells, K padded from 250 to 256 and K = 256 exactly, several sequence groups polling one counter."""
+    import currennt_b200 as cb
+    name, net_json, S, lengths, classes, G = case
+    monkeypatch.setenv("BLSTM_REC_V", "3")
+    if G:
+        monkeypatch.setenv("BLSTM_FWD_G", str(G))
+    info = cb.Net(gpu_ctx, net_json, S, max(lengths) + 2).plan_info(1)
+    assert info["fwd_kernel"] == "tmem", info
+    worst = check_net(oracle, gpu_ctx, net_json, S, lengths, classes, 0, seed=13)
+    print(name, info, "worst rel err %.2e" % worst)
+
+
+def test_tensor_memory_kernel_falls_back_when_weights_do_not_fit(gpu_ctx, monkeypatch):
+    """pad32(H) > 256 does not fit the 512 TMEM columns: BLSTM_REC_V=3 then keeps the register / shared-memory kernels."""
+    import currennt_b200 as cb
+    monkeypatch.setenv("BLSTM_REC_V", "3")
+    info = cb.Net(gpu_ctx, synth.network_json(9, [("lstm", 300)], 4), 2, 6).plan_info(1)
+    assert info["fwd_kernel"] != "tmem", info
 
 
 def test_extreme_shapes(oracle, gpu_ctx):
@@ -400,15 +441,64 @@ def _full_net(gpu_ctx, name, S, maxT):
     return cfg, net, weights
 
 
-def test_c2_network_against_oracle_short_sequences(oracle, gpu_ctx):
+@pytest.mark.parametrize("family", ["default", "tmem"])
+def test_c2_network_against_oracle_short_sequences(oracle, gpu_ctx, family, monkeypatch):
     """The full TIMIT-shape network (123 -> 3 x blstm 500 -> softmax 183, S=100) against the oracle on a fraction short enough
     for the CPU oracle (T=10): every tensor within the strict bar.  Exercises the production geometry (G=9 x C=8 slices,
     register-resident weights) and the tcgen05 GEMMs at their real M/N."""
+    if family == "tmem":                       # forward step GEMM on tcgen05, weights in tensor memory (G=9 x C=8, N=16, K=256)
+        monkeypatch.setenv("BLSTM_REC_V", "3")
     cfg = synth.config("C2")
     rng = np.random.default_rng(3)
     lengths = sorted(rng.integers(6, 11, 100).tolist())
     worst = check_net(oracle, gpu_ctx, cfg["net"], 100, lengths, 183, 0, seed=21)
-    print("C2 full-width worst rel err %.2e" % worst)
+    print("C2 full-width (%s) worst rel err %.2e" % (family, worst))
+
+
+def test_c3_chime_recognition_shape_against_oracle(oracle, gpu_ctx):
+    """BASELINE config 3: the CHiME recognition recipe's network (39 -> blstm 156 -> blstm 300 -> blstm 102 -> softmax 51,
+    S=50, examples/speech_recognition_chime/no_subsampling/network.jsn) at full width on sequences short enough for the oracle."""
+    cfg = synth.config("C3")
+    rng = np.random.default_rng(3)
+    lengths = sorted(rng.integers(5, 13, 50).tolist())
+    worst = check_net(oracle, gpu_ctx, cfg["net"], 50, lengths, 51, 0, seed=31)
+    print("C3 full-width worst rel err %.2e" % worst)
+
+
+def test_c4_chime_autoencoding_truncated_against_oracle(oracle, gpu_ctx):
+    """BASELINE config 4: the CHiME autoencoding recipe (39 -> 156 -> 256 -> 156 -> feedforward_identity 39 -> sse,
+    truncate_seq=64, S=50).  13 noisy/clean sequences of 113..152 frames are cut by the product's DataSet into 26 chunks
+    (64 + 49..88, DataSet.cpp:527-542) and sorted; chunk lengths must equal the oracle's rule exactly, and the resulting
+    fraction (S=50 with 24 empty columns, T up to 88) must match the oracle on every tensor."""
+    import currennt_b200 as cb
+    cfg = synth.config("C4")
+    S = cfg["S"]
+    lengths = synth.sequence_lengths(cfg, 13, 4)
+    xs, _, ts = synth.make_sequences(lengths, 39, 4, target_size=39)
+    ds = cb.DataSet(gpu_ctx, xs, S, seq_targets=ts, truncate=cfg["truncate"], training=True)
+    chunks = oracle.truncate_lengths(lengths, cfg["truncate"])
+    assert ds.total_sequences == len(chunks) == 26 and ds.total_timesteps == int(lengths.sum())
+    assert sorted(ds.sequence_lengths().tolist()) == sorted(chunks)                # packing is bit-exact
+    pf = ds.next_fraction()
+    assert ds.next_fraction() is None
+    inputs, pat, _, tg, lens = pf.arrays(False)
+    assert pf.T == max(chunks) and pf.Tmin == min(chunks) and lens.tolist() == sorted(chunks)
+    frac = oracle.Fraction(S, pf.T, pf.Tmin, lens, 39, 39, inputs, pat, None, tg)
+    weights = synth.init_weights(cfg["net"], 41)
+    orc, gpu = oracle.OracleNet(cfg["net"], S, pf.T), cb.Net(gpu_ctx, cfg["net"], S, pf.T)
+    worst = compare_nets(orc, gpu, weights, frac, json.loads(cfg["net"])["layers"], S)
+    print("C4 truncated fraction worst rel err %.2e" % worst)
+
+
+def test_c5_lvcsr_shape_against_oracle(oracle, gpu_ctx):
+    """BASELINE config 5: the LVCSR-shape network (123 -> 5 x blstm 1024 (512 cells/direction) -> softmax 8000) with the
+    per-GPU share of the global S=128 (16 sequences), on sequences of 2..3 frames so that the CPU oracle finishes in seconds.
+    Exercises the H=512 recurrent geometry and the 8000-wide softmax / multiclass objective."""
+    cfg = synth.config("C5")
+    rng = np.random.default_rng(5)
+    lengths = sorted(rng.integers(2, 4, 16).tolist())
+    worst = check_net(oracle, gpu_ctx, cfg["net"], 16, lengths, 8000, 0, seed=51)
+    print("C5 full-width worst rel err %.2e" % worst)
 
 
 def test_c2_full_size_properties(gpu_ctx):
