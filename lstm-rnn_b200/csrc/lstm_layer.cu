@@ -27,7 +27,7 @@ struct bl_lstm_plan {
     float bias;
     bl::RecGeom gf, gb;
     bool reg_f, reg_b;       // register-resident persistent kernels (lstm_recurrent_reg.cu) vs shared-memory ones
-    bool tm_f;               // forward: tensor-memory-resident weights + tcgen05 step GEMM (lstm_recurrent_tmem.cu)
+    bool tm_f, tm_b;         // tensor-memory-resident weights + tcgen05 step GEMM (lstm_recurrent_tmem.cu)
     float *acts, *deltas, *cst, *cerr, *hx, *dx, *gpart;
     long long *trace;
     float *tcbuf;            // prepared tensor-core operands (hi then lo of each): X, Win (forward); deltas, Y, Win re-blocked (backward)
@@ -136,9 +136,10 @@ int bl_lstm_plan_create(bl_ctx *ctx, int P, int L, int bidirectional, int S, int
     const bool want_reg = family != 2;
     pl->tm_f = family == 3 && bl::choose_geometry_tmem(pl->H, S, pl->ndir, ctx->num_sms, cap, ef ? atoi(ef) : 0, &pl->gf);
     pl->reg_f = !pl->tm_f && want_reg && bl::choose_geometry_reg(false, pl->H, S, pl->ndir, ctx->num_sms, cap, ef ? atoi(ef) : 0, &pl->gf);
-    pl->reg_b = want_reg && bl::choose_geometry_reg(true, pl->H, S, pl->ndir, ctx->num_sms, cap, eb ? atoi(eb) : 0, &pl->gb);
+    pl->tm_b = family == 3 && bl::choose_geometry_tmem_bwd(pl->H, S, pl->ndir, ctx->num_sms, cap, eb ? atoi(eb) : 0, &pl->gb);
+    pl->reg_b = !pl->tm_b && want_reg && bl::choose_geometry_reg(true, pl->H, S, pl->ndir, ctx->num_sms, cap, eb ? atoi(eb) : 0, &pl->gb);
     if ((!pl->tm_f && !pl->reg_f && !bl::choose_geometry(false, pl->H, S, pl->ndir, ctx->num_sms, cap, ef ? atoi(ef) : 0, nf ? atoi(nf) : 0, tf ? atoi(tf) : 0, &pl->gf)) ||
-        (!pl->reg_b && !bl::choose_geometry(true, pl->H, S, pl->ndir, ctx->num_sms, cap, eb ? atoi(eb) : 0, nb ? atoi(nb) : 0, tb ? atoi(tb) : 0, &pl->gb))) {
+        (!pl->tm_b && !pl->reg_b && !bl::choose_geometry(true, pl->H, S, pl->ndir, ctx->num_sms, cap, eb ? atoi(eb) : 0, nb ? atoi(nb) : 0, tb ? atoi(tb) : 0, &pl->gb))) {
         delete pl;
         return bl::fail(ctx, "bl_lstm_plan_create: no persistent-kernel geometry fits (H=%d S=%d): recurrent weights do not fit on chip",
                         L / (bidirectional ? 2 : 1), S);
@@ -186,7 +187,8 @@ int bl_lstm_plan_info(const bl_lstm_plan *pl, int *o)
     // (the tensor-memory forward kernel reports its smem rounded up to 16 with 11 in the low four bits)
     o[0] = pl->gf.G; o[1] = pl->gf.C; o[2] = pl->gf.CL;
     o[3] = pl->tm_f ? (int)((pl->gf.smem + 15) & ~(size_t)15) + 11 : (int)pl->gf.smem + (pl->reg_f ? 3 : pl->gf.nsub);
-    o[4] = pl->gb.G; o[5] = pl->gb.C; o[6] = pl->gb.CL; o[7] = (int)pl->gb.smem + (pl->reg_b ? 3 : pl->gb.nsub);
+    o[4] = pl->gb.G; o[5] = pl->gb.C; o[6] = pl->gb.CL;
+    o[7] = pl->tm_b ? (int)((pl->gb.smem + 15) & ~(size_t)15) + 11 : (int)pl->gb.smem + (pl->reg_b ? 3 : pl->gb.nsub);
     return 0;
 }
 
@@ -276,13 +278,13 @@ int bl_lstm_backward(bl_lstm_plan *pl, const float *W, const float *X, int ldx, 
     p.dx = pl->dx; p.flags = pl->flags_b; p.pat = patTypes;
     p.T = T; p.Tmin = Tmin; p.S = S; p.H = H; p.L = L; p.ndir = pl->ndir; p.g = pl->gb;
     const bool tc = bl::tc_wanted(ctx, P, 4 * L, N);
-    const bool fused_dsplit = tc && pl->reg_b && getenv("BLSTM_NO_FUSED_SPLIT") == nullptr;
+    const bool fused_dsplit = tc && (pl->reg_b || pl->tm_b) && getenv("BLSTM_NO_FUSED_SPLIT") == nullptr;
     p.ds_hi = p.ds_lo = nullptr; p.ld_ds = 0;
     if (fused_dsplit) {
         BL_CHECK(plan_tc_buffers(pl));
         p.ds_hi = pl->tc_D; p.ds_lo = pl->tc_D + pl->tc_eD; p.ld_ds = (int)bl::tc_operand_ld(4 * pl->ndir * ((H + 3) & ~3));
     }
-    BL_CHECK(pl->reg_b ? bl::launch_lstm_bwd_reg(ctx, p) : bl::launch_lstm_bwd(ctx, p));
+    BL_CHECK(pl->tm_b ? bl::launch_lstm_bwd_tmem(ctx, p) : pl->reg_b ? bl::launch_lstm_bwd_reg(ctx, p) : bl::launch_lstm_bwd(ctx, p));
 
     if (tc) {
         // ---- tensor-core path: every operand is split (hi/lo TF32) ONCE per layer, in its own row-major layout, and read

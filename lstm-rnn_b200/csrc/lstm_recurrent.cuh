@@ -68,9 +68,11 @@ bool choose_geometry_reg(bool bwd, int H, int S, int ndir, int num_sms, int smem
 int launch_lstm_fwd_reg(bl_ctx *ctx, const RecFwdParams &p);
 int launch_lstm_bwd_reg(bl_ctx *ctx, const RecBwdParams &p);
 
-// tensor-memory-resident forward variant (lstm_recurrent_tmem.cu): weights in TMEM, step GEMM on tcgen05; pad32(H) <= 256 only
+// tensor-memory-resident variants (lstm_recurrent_tmem.cu): weights in TMEM, step GEMM on tcgen05; pad32(H) <= 256 only
 bool choose_geometry_tmem(int H, int S, int ndir, int num_sms, int smem_cap, int forceG, RecGeom *out);
 int launch_lstm_fwd_tmem(bl_ctx *ctx, const RecFwdParams &p);
+bool choose_geometry_tmem_bwd(int H, int S, int ndir, int num_sms, int smem_cap, int forceG, RecGeom *out);
+int launch_lstm_bwd_tmem(bl_ctx *ctx, const RecBwdParams &p);
 
 int launch_lstm_fwd(bl_ctx *ctx, const RecFwdParams &p);
 int launch_lstm_bwd(bl_ctx *ctx, const RecBwdParams &p);

@@ -402,9 +402,298 @@ __global__ void __launch_bounds__(TM_NT, 1) lstm_fwd_tmem_kernel(const RecFwdPar
     }
 }
 
+// ------------------------------------------------------------------------------------------------ BPTT
+// Output-stationary slicing: the CTA that owns the cells j of a slice has just produced their four gate deltas, so it multiplies
+// THOSE (K = 4 gates x 32 cells = 128, straight from registers into the B tiles -- no exchange read for the GEMM operand) with
+// the weight columns of ALL source cells k' of its direction (M = pad128(H) rows = 1 or 2 TMEM tiles):
+//     Q[k', s] = sum_{gate, j in slice} W_gate[j, k'] * delta_gate[j, s]           A[k'][gate*32 + c] = Wi[gate*L*H + d*H*H + (j0+c)*H + k']
+// and publishes its partial Q through the L2 exchange buffer; next step every CTA adds the C partials of its own cells
+// (fixed order, so the result is deterministic) to the output error -- the 4 addProducts of LstmLayer.cu:939-942.  Per step and CTA
+// that is C*CL*SG floats read (12 KB at C2) instead of the 4*Hp*SG (48 KB) the cell-stationary kernels read, and the same 80 MMAs
+// as the forward kernel.  Exchange layout: [dir][parity][group][producer slice][sequence NB][k' R], R = pad128(H).
+bool choose_geometry_tmem_bwd(int H, int S, int ndir, int num_sms, int smem_cap, int forceG, RecGeom *out)
+{
+    if (tm_pad32(H) > 256) return false;
+    const int R = (H + 127) / 128 * 128;
+    const int per_dir = num_sms / ndir;
+    bool found = false;
+    RecGeom best{};
+    for (int G = 1; G <= 64 && G <= S; ++G) {
+        if (forceG > 0 && G != forceG) continue;
+        int C = per_dir / G;
+        if (C < 1) break;
+        const int CL = cdiv(H, C);
+        if (CL > 32) continue;
+        C = cdiv(H, CL);
+        const int SG = cdiv(S, G);
+        if ((G - 1) * SG >= S) continue;
+        if (SG > 32) continue;
+        const int NB = SG <= 16 ? 16 : 32;
+        if (CL * SG > REC_NPAIR * TM_NT) continue;
+        const size_t smem = (size_t)2 * 4 * NB * 128 + (size_t)2 * NB * 128 + 1024;
+        if ((int)smem > smem_cap) continue;
+        const int npair = (CL * SG > TM_NT) ? 2 : 1;
+        const double mma = (R / 128) * 40.0 * (NB == 16 ? 20.0 : 28.0) + 300.0;
+        const double gate = 1000.0 + 700.0 * npair;
+        const double xchg = 40.0 * C + (double)R * SG * 4.0 / 64.0 + 500.0;
+        const double cost = mma + gate + xchg + 1500.0;
+        if (!found || cost < best.cost) {
+            found = true;
+            best = RecGeom{};
+            best.G = G; best.C = C; best.CL = CL; best.SG = SG; best.NT = TM_NT; best.nsub = 1; best.npair = npair;
+            best.R = R; best.Hpad = R; best.Spad = NB; best.smem = smem; best.cost = cost;
+            // the plan allocates ndir*2*S*RS floats for the exchange buffer: make that cover [G][C][NB][R] per (dir, parity)
+            best.RS = (int)(((size_t)G * C * NB * R + S - 1) / S);
+        }
+    }
+    if (found) *out = best;
+    return found;
+}
+
+template <int NPAIR>
+__global__ void __launch_bounds__(TM_NT, 1) lstm_bwd_tmem_kernel(const RecBwdParams p)
+{
+    extern __shared__ uint8_t tm_smem_raw[];
+    __shared__ unsigned long long s_tab[32];
+    __shared__ uint64_t s_bar;
+    __shared__ uint32_t s_slot;
+    const RecGeom &g = p.g;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int R = g.Hpad, MT = R / 128, NB = g.Spad;
+    const int bhi_bytes = 4 * NB * 128, bbf_bytes = 2 * NB * 128;          // K = 128: 4 K-blocks of 32 floats, 2 of 64 bf16
+    uint8_t *base = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(tm_smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t *Bhi = base, *Blo = base + bhi_bytes, *Bbf = base + 2 * bhi_bytes;
+
+    const int H = p.H, L = p.L, S = p.S, T = p.T;
+    const int d = blockIdx.x / (g.G * g.C);
+    const int grp = (blockIdx.x % (g.G * g.C)) / g.C;
+    const int cs = blockIdx.x % g.C;
+    const int j0 = cs * g.CL, ncell = min(g.CL, H - j0);
+    const int s0 = grp * g.SG, nseq = min(g.SG, S - s0);
+    unsigned *flag = p.flags + (d * g.G + grp) * 32;
+    const bool inplace = (p.ndir == 1);
+
+    // B entries of cells beyond ncell / sequences beyond nseq are never written: they stay zero for the whole pass
+    for (int i = tid; i < (2 * bhi_bytes + bbf_bytes) / 4; i += TM_NT) reinterpret_cast<uint32_t *>(base)[i] = 0u;
+    if (tid < 32) s_tab[tid] = bl_exp2f_tab[tid];
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(tm_smem_u32(&s_bar)), "r"(1) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 5) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(tm_smem_u32(&s_slot)), "n"(TM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem = s_slot;
+
+    // weights into TMEM, once.  Tile mt, lane = source cell k' - mt*128, column = gate*32 + c (tf32 hi at mt*128, bf16 lo pairs at 256 + mt*64)
+    if (warp < 4) {
+        const uint32_t lane_base = tmem + ((uint32_t)(warp * 32) << 16);
+        for (int mt = 0; mt < MT; ++mt) {
+            const int kr = mt * 128 + warp * 32 + lane;
+            const bool ok = kr < H;
+            const float *w = p.Wi + (size_t)d * H * H + (size_t)j0 * H + (ok ? kr : 0);
+            for (int c0 = 0; c0 < 128; c0 += 8) {
+                uint32_t r[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const int kk = c0 + i, gi = kk >> 5, c = kk & 31;
+                    r[i] = (ok && c < ncell) ? __float_as_uint(tm_tf32(__ldg(w + (size_t)gi * L * H + (size_t)c * H))) : 0u;
+                }
+                tm_st8(lane_base + TM_COL_AHI + mt * 128 + c0, r);
+            }
+            for (int c0 = 0; c0 < 64; c0 += 8) {
+                uint32_t r[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const int kk = 2 * (c0 + i), gi = kk >> 5, c = kk & 31;      // kk even: kk and kk+1 share the gate
+                    const float x0 = (ok && c < ncell) ? __ldg(w + (size_t)gi * L * H + (size_t)c * H) : 0.0f;
+                    const float x1 = (ok && c + 1 < ncell) ? __ldg(w + (size_t)gi * L * H + (size_t)(c + 1) * H) : 0.0f;
+                    r[i] = tm_bf16(__fsub_rn(x0, tm_tf32(x0))) | (tm_bf16(__fsub_rn(x1, tm_tf32(x1))) << 16);
+                }
+                tm_st8(lane_base + TM_COL_ALO + mt * 64 + c0, r);
+            }
+        }
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+    }
+
+    bool valid[NPAIR]; int cl_[NPAIR], sl_[NPAIR];
+    float wpe[NPAIR][3];
+    float nfg[NPAIR], ncerr[NPAIR], ndig[NPAIR], ndfg[NPAIR];   // "next step" state, :253-256
+#pragma unroll
+    for (int u = 0; u < NPAIR; ++u) {
+        const int pr = tid + u * TM_NT;
+        cl_[u] = pr % g.CL; sl_[u] = pr / g.CL;
+        valid[u] = (cl_[u] < ncell) && (sl_[u] < nseq);
+        nfg[u] = ncerr[u] = ndig[u] = ndfg[u] = 0.0f;
+        if (valid[u]) {
+            const int col = d * H + j0 + cl_[u];
+#pragma unroll
+            for (int gi = 0; gi < 3; ++gi) wpe[u][gi] = __ldg(p.Wp + gi * L + col);
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+
+    const uint32_t idesc_tf32 = tm_make_idesc(2u, NB), idesc_bf16 = tm_make_idesc(1u, NB);
+    const uint64_t desc_hi = tm_make_desc(Bhi), desc_lo = tm_make_desc(Blo), desc_bf = tm_make_desc(Bbf);
+    const uint64_t kb_step = (uint64_t)((NB * 128) >> 4);
+    const size_t ex_slice = (size_t)NB * R;                      // one producer's [NB][R] block
+
+    for (int q = 0; q < T; ++q) {
+        const int t = (d == 0) ? T - 1 - q : q;                 // fw walks time backwards, bw forwards (:936, :970)
+        const bool firstCall = (q == 0);
+        const bool lastCall = (q == T - 1);
+        const bool check = (t >= p.Tmin);
+        const int tprev = (d == 0) ? t - 1 : t + 1;
+        const float *acts_t = p.acts + (size_t)t * S * 4 * L + d * H + j0;
+        const float *cst_t = p.cst + (size_t)t * S * L + d * H + j0;
+        const float *cst_p = p.cst + (size_t)(lastCall ? t : tprev) * S * L + d * H + j0;
+        float *dy_t = p.dY + (size_t)t * S * p.lddy + d * H + j0;
+        float *del_t = p.deltas + (size_t)t * S * 4 * L + d * H + j0;
+        float *cerr_t = p.cerr + (size_t)t * S * L + d * H + j0;
+        const char *pat_t = p.pat + (size_t)t * S;
+        float *ex_w = p.dx + (((size_t)(d * 2 + (q & 1)) * g.G + grp) * g.C + cs) * ex_slice;
+
+        float a[NPAIR][4], c[NPAIR], cp[NPAIR], oe[NPAIR], r_dni[NPAIR], r_dog[NPAIR], esum[NPAIR]; bool dummy[NPAIR];
+#pragma unroll
+        for (int u = 0; u < NPAIR; ++u) {
+            dummy[u] = false; cp[u] = 0.0f; r_dni[u] = r_dog[u] = 0.0f; esum[u] = 0.0f;
+            if (valid[u]) {
+                const int slot = s0 + sl_[u], cl = cl_[u];
+                dummy[u] = check && (pat_t[slot] == BL_PATTYPE_NONE);
+#pragma unroll
+                for (int gi = 0; gi < 4; ++gi) a[u][gi] = acts_t[slot * 4 * L + gi * L + cl];
+                c[u] = cst_t[slot * L + cl];
+                if (!lastCall) cp[u] = cst_p[slot * L + cl];
+                oe[u] = dy_t[slot * p.lddy + cl];
+            }
+        }
+
+        if (!firstCall) {
+            tm_wait_warp(flag, (unsigned)(g.C * q));
+            // the partial products of all C producers of this (direction, group) for this thread's cell, in slice order
+            const float *ex_r = p.dx + (((size_t)(d * 2 + ((q - 1) & 1)) * g.G + grp) * g.C) * ex_slice;
+#pragma unroll
+            for (int u = 0; u < NPAIR; ++u) {
+                if (!valid[u]) continue;
+                const float *rp = ex_r + (size_t)sl_[u] * R + j0 + cl_[u];
+                float s = 0.0f;
+#pragma unroll 8
+                for (int pp = 0; pp < g.C; ++pp) s = __fadd_rn(s, __ldcg(rp + (size_t)pp * ex_slice));
+                esum[u] = s;
+            }
+        }
+
+#pragma unroll
+        for (int u = 0; u < NPAIR; ++u) {
+            if (!valid[u]) continue;
+            const int slot = s0 + sl_[u], cl = cl_[u];
+            float e = oe[u];
+            if (!firstCall) e = __fadd_rn(e, esum[u]);           // the 4 addProducts of :939-942
+            if (inplace) dy_t[slot * p.lddy + cl] = e;           // unidirectional: tmpOutputErrors IS outputErrors (:907-910)
+            float dni, dig, dfg, dog, cerr;
+            if (dummy[u]) {                                       // :224-234
+                dni = dig = dfg = dog = cerr = 0.0f;
+                nfg[u] = 0.0f;
+            } else {
+                const float ni = a[u][0], ig = a[u][1], fg = a[u][2], og = a[u][3];
+                const float tc = tanh_fn_tab(c[u], s_tab);
+                dog = __fmul_rn(__fmul_rn(logistic_deriv(og), tc), e);                                   // :246
+                cerr = __fadd_rn(__fmul_rn(__fmul_rn(og, tanh_deriv(tc)), e), __fmul_rn(wpe[u][2], dog)); // :250
+                if (!firstCall)                                                                            // :252-262
+                    cerr = __fadd_rn(cerr, __fadd_rn(__fadd_rn(__fmul_rn(nfg[u], ncerr[u]), __fmul_rn(wpe[u][0], ndig[u])),
+                                                     __fmul_rn(wpe[u][1], ndfg[u])));
+                dni = __fmul_rn(__fmul_rn(ig, tanh_deriv(ni)), cerr);                                    // :265
+                dfg = lastCall ? 0.0f : __fmul_rn(__fmul_rn(logistic_deriv(fg), cp[u]), cerr);           // :268-275
+                dig = __fmul_rn(__fmul_rn(logistic_deriv(ig), ni), cerr);                                // :278
+                dni = limited_error(dni); dig = limited_error(dig);                                      // :281-284
+                dfg = limited_error(dfg); dog = limited_error(dog);
+                nfg[u] = fg;
+            }
+            ncerr[u] = cerr; ndig[u] = dig; ndfg[u] = dfg;
+            r_dni[u] = dni; r_dog[u] = dog;
+            if (!lastCall) {                                     // B operand of this step's product: k = gate*32 + cell, row = sequence
+                const float dv[4] = {dni, dig, dfg, dog};
+#pragma unroll
+                for (int gi = 0; gi < 4; ++gi) {
+                    const float hi = tm_tf32(dv[gi]);
+                    const int of = tm_off_f32(NB, sl_[u], gi * 32 + cl);
+                    *reinterpret_cast<float *>(Bhi + of) = hi;
+                    *reinterpret_cast<float *>(Blo + of) = __fsub_rn(dv[gi], hi);
+                    *reinterpret_cast<unsigned short *>(Bbf + tm_off_bf16(NB, sl_[u], gi * 32 + cl)) = (unsigned short)tm_bf16(dv[gi]);
+                }
+            }
+        }
+        if (!lastCall) {
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncthreads();
+            if (warp == 4) {
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                if (tm_elect_one()) {
+                    for (int mt = 0; mt < MT; ++mt) {
+                        const uint32_t dcol = tmem + TM_COL_D + mt * NB;
+                        uint32_t acc = 0u;                     // small terms first, then the leading one
+                        for (int ks = 0; ks < 8; ++ks) {       // bf16: K = 128 = 8 MMAs of 16
+                            tm_mma_bf16(dcol, tmem + TM_COL_ALO + mt * 64 + ks * 8, desc_bf + (uint64_t)(ks >> 2) * kb_step + (uint64_t)((ks & 3) * 2), idesc_bf16, acc);
+                            acc = 1u;
+                        }
+                        for (int ks = 0; ks < 16; ++ks)        // tf32: K = 128 = 16 MMAs of 8
+                            tm_mma_tf32(dcol, tmem + TM_COL_AHI + mt * 128 + ks * 8, desc_lo + (uint64_t)(ks >> 2) * kb_step + (uint64_t)((ks & 3) * 2), idesc_tf32, 1u);
+                        for (int ks = 0; ks < 16; ++ks)
+                            tm_mma_tf32(dcol, tmem + TM_COL_AHI + mt * 128 + ks * 8, desc_hi + (uint64_t)(ks >> 2) * kb_step + (uint64_t)((ks & 3) * 2), idesc_tf32, 1u);
+                    }
+                    tm_commit(&s_bar);
+                }
+                __syncwarp();
+            }
+            if (warp < 4) {
+                tm_mbar_wait(&s_bar, (uint32_t)(q & 1));
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                for (int mt = 0; mt < MT; ++mt)
+                    for (int cc = 0; cc < NB; cc += 16) {
+                        float dv[16];
+                        tm_ld16(tmem + ((uint32_t)(warp * 32) << 16) + TM_COL_D + mt * NB + cc, dv);
+#pragma unroll
+                        for (int i = 0; i < 16; ++i)
+                            if (cc + i < nseq) ex_w[(size_t)(cc + i) * R + mt * 128 + warp * 32 + lane] = dv[i];
+                    }
+                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            }
+            tm_publish(flag);
+        }
+#pragma unroll
+        for (int u = 0; u < NPAIR; ++u) {                        // HBM-only results after the publish
+            if (!valid[u]) continue;
+            const int slot = s0 + sl_[u], cl = cl_[u];
+            float *dp = del_t + slot * 4 * L + cl;
+            dp[0] = r_dni[u]; dp[L] = ndig[u]; dp[2 * L] = ndfg[u]; dp[3 * L] = r_dog[u];
+            cerr_t[slot * L + cl] = ncerr[u];
+            if (p.ds_hi) {
+                const int Hq = (H + 3) & ~3;
+                const size_t bs = ((size_t)t * S + slot) * p.ld_ds + (size_t)d * Hq + j0 + cl, gs = (size_t)p.ndir * Hq;
+                tm_split_store(p.ds_hi, p.ds_lo, bs, r_dni[u]); tm_split_store(p.ds_hi, p.ds_lo, bs + gs, ndig[u]);
+                tm_split_store(p.ds_hi, p.ds_lo, bs + 2 * gs, ndfg[u]); tm_split_store(p.ds_hi, p.ds_lo, bs + 3 * gs, r_dog[u]);
+            }
+        }
+    }
+
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 5) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem), "n"(TM_COLS) : "memory");
+    }
+}
+
 // ------------------------------------------------------------------------------------------------ launch
-template <typename Kernel>
-static int launch_tmem(bl_ctx *ctx, Kernel kernel, const RecFwdParams &p)
+template <typename Params, typename Kernel>
+static int launch_tmem(bl_ctx *ctx, Kernel kernel, const Params &p, const char *name)
 {
     const RecGeom &g = p.g;
     const int grid = p.ndir * g.G * g.C;
@@ -412,7 +701,7 @@ static int launch_tmem(bl_ctx *ctx, Kernel kernel, const RecFwdParams &p)
     int per_sm = 0;
     BL_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, TM_NT, g.smem));
     if (per_sm < 1 || grid > per_sm * ctx->num_sms)
-        return fail(ctx, "lstm_fwd_tmem: %d CTAs cannot be co-resident (%d per SM x %d SMs)", grid, per_sm, ctx->num_sms);
+        return fail(ctx, "%s: %d CTAs cannot be co-resident (%d per SM x %d SMs)", name, grid, per_sm, ctx->num_sms);
     BL_CUDA(ctx, cudaMemsetAsync(p.flags, 0, (size_t)p.ndir * g.G * 32 * sizeof(unsigned), ctx->stream));
     void *args[] = { (void *)&p };
     BL_CUDA(ctx, cudaLaunchCooperativeKernel((const void *)kernel, dim3(grid), dim3(TM_NT), args, g.smem, ctx->stream));
@@ -423,7 +712,13 @@ static int launch_tmem(bl_ctx *ctx, Kernel kernel, const RecFwdParams &p)
 int launch_lstm_fwd_tmem(bl_ctx *ctx, const RecFwdParams &p)
 {
     TimedRegion timed(ctx, 1);
-    return p.g.npair == 1 ? launch_tmem(ctx, lstm_fwd_tmem_kernel<1>, p) : launch_tmem(ctx, lstm_fwd_tmem_kernel<2>, p);
+    return p.g.npair == 1 ? launch_tmem(ctx, lstm_fwd_tmem_kernel<1>, p, "lstm_fwd_tmem") : launch_tmem(ctx, lstm_fwd_tmem_kernel<2>, p, "lstm_fwd_tmem");
+}
+
+int launch_lstm_bwd_tmem(bl_ctx *ctx, const RecBwdParams &p)
+{
+    TimedRegion timed(ctx, 2);
+    return p.g.npair == 1 ? launch_tmem(ctx, lstm_bwd_tmem_kernel<1>, p, "lstm_bwd_tmem") : launch_tmem(ctx, lstm_bwd_tmem_kernel<2>, p, "lstm_bwd_tmem");
 }
 
 } // namespace bl

@@ -189,7 +189,7 @@ def test_both_recurrent_kernel_families(oracle, gpu_ctx, family, monkeypatch):
         monkeypatch.setenv("BLSTM_REC_V", "3")
     net_json = synth.network_json(13, [48, ("lstm", 27)], 11)
     info = cb.Net(gpu_ctx, net_json, 6, 16).plan_info(1)
-    assert info["fwd_kernel"] == family and info["bwd_kernel"] == ("registers" if family == "tmem" else family), info
+    assert info["fwd_kernel"] == family and info["bwd_kernel"] == family, info
     worst = check_net(oracle, gpu_ctx, net_json, 6, [1, 4, 9, 9, 12, 14], 11, 0, seed=21)
     print(family, "worst rel err %.2e" % worst)
 
@@ -206,16 +206,18 @@ TMEM_CASES = [
 
 
 @pytest.mark.parametrize("case", TMEM_CASES, ids=[c[0] for c in TMEM_CASES])
-def test_tensor_memory_forward_kernel(oracle, gpu_ctx, case, monkeypatch):
-    """lstm_fwd_tmem_kernel (BLSTM_REC_V=3) against the oracle at the strict bar: N=16 and N=32 tiles, slices with fewer than 32
-    cells, K padded from 250 to 256 and K = 256 exactly, several sequence groups polling one counter."""
+def test_tensor_memory_recurrent_kernels(oracle, gpu_ctx, case, monkeypatch):
+    """lstm_fwd_tmem_kernel / lstm_bwd_tmem_kernel (BLSTM_REC_V=3) against the oracle at the strict bar: N=16 and N=32 tiles, slices
+    with fewer than 32 cells, K padded from 250 to 256 and K = 256 exactly (two 128-row tiles in the BPTT kernel), one and several
+    sequence groups."""
     import currennt_b200 as cb
     name, net_json, S, lengths, classes, G = case
     monkeypatch.setenv("BLSTM_REC_V", "3")
     if G:
         monkeypatch.setenv("BLSTM_FWD_G", str(G))
+        monkeypatch.setenv("BLSTM_BWD_G", str(G))
     info = cb.Net(gpu_ctx, net_json, S, max(lengths) + 2).plan_info(1)
-    assert info["fwd_kernel"] == "tmem", info
+    assert info["fwd_kernel"] == "tmem" and info["bwd_kernel"] == "tmem", info
     worst = check_net(oracle, gpu_ctx, net_json, S, lengths, classes, 0, seed=13)
     print(name, info, "worst rel err %.2e" % worst)
 
@@ -225,7 +227,7 @@ def test_tensor_memory_kernel_falls_back_when_weights_do_not_fit(gpu_ctx, monkey
     import currennt_b200 as cb
     monkeypatch.setenv("BLSTM_REC_V", "3")
     info = cb.Net(gpu_ctx, synth.network_json(9, [("lstm", 300)], 4), 2, 6).plan_info(1)
-    assert info["fwd_kernel"] != "tmem", info
+    assert info["fwd_kernel"] != "tmem" and info["bwd_kernel"] != "tmem", info
 
 
 def test_extreme_shapes(oracle, gpu_ctx):
