@@ -303,7 +303,9 @@ def run_ours(args, rank, world, local_rank):
         if os.path.exists(tpath):        # DRAM bytes per slot and unit of layer size from the committed ncu --set full captures
             tj = json.load(open(tpath))
             traffic = (fwd_b / 40.0 * tj["fwd_dram_bytes_per_slot_per_layer_unit"] + bwd_b / 48.0 * tj["bwd_dram_bytes_per_slot_per_layer_unit"]) / max(n_launch, 1)
-        roofline = {"kernel": "lstm_{fwd,bwd}_reg_kernel", "bound": "hbm", "achieved": achieved, "peak": pk["hbm_gbs"], "unit": "GB/s",
+        plan = net.plan_info(2)
+        kfam = {"tmem": "tmem", "registers": "reg", "smem": "persistent"}
+        roofline = {"kernel": "lstm_fwd_%s_kernel + lstm_bwd_%s_kernel" % (kfam[plan["fwd_kernel"]], kfam[plan["bwd_kernel"]]), "bound": "hbm", "achieved": achieved, "peak": pk["hbm_gbs"], "unit": "GB/s",
                     "frac": achieved / pk["hbm_gbs"], "peak_source": pk["source"], "traffic": traffic,
                     "algorithmic_bytes_per_launch": (fwd_b + bwd_b) / max(n_launch, 1), "avg_launch_ms": rec_ms / max(n_launch, 1),
                     "share_of_kernel_time": share[1] + share[2]}
@@ -315,7 +317,7 @@ def run_ours(args, rank, world, local_rank):
                 "config": {"workload": WORKLOAD["C2"], "parallel_sequences_per_gpu": S, "gemm_mode": args.mode,
                            "frames_per_step": total_frames / K, "slots_per_step_per_gpu": slots / K,
                            "l2": "inputs larger than L2: every step touches ~%.1f GB of activations/deltas per GPU" % (slots / K * 2000 * 4 * 2 * 3 / 1e9),
-                           "plan": net.plan_info(2)},
+                           "plan": plan},
                 "e2e": {"value": total_frames / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 8},
                 "device_ms_per_step": dev_ms / K, "gpu_launches": launches, "clocks": clocks, "roofline": roofline,
                 "kernel_classes": classes}

@@ -128,15 +128,15 @@ int bl_lstm_plan_create(bl_ctx *ctx, int P, int L, int bidirectional, int S, int
 
     const int cap = ctx->smem_optin - 2048;      // room for the kernels' static shared memory (exp table) and the driver's reserve
     // tuning overrides (tools/sweep_geometry.py): sequence groups / sub-CTAs / threads of either kernel, and the kernel family
-    // (BLSTM_REC_V=2 forces the shared-memory-resident kernels, BLSTM_REC_V=3 selects the tensor-memory-resident forward kernel
-    // where it fits; default: register-resident weights whenever the slice fits)
+    // (default: tensor-memory-resident weights + tcgen05 step GEMM where the slice fits the 512 TMEM columns, else register-resident
+    // weights, else shared memory; BLSTM_REC_V=1 skips the tensor-memory kernels, BLSTM_REC_V=2 forces the shared-memory ones)
     const char *ef = getenv("BLSTM_FWD_G"), *eb = getenv("BLSTM_BWD_G"), *nf = getenv("BLSTM_FWD_NSUB"), *nb = getenv("BLSTM_BWD_NSUB"),
                *tf = getenv("BLSTM_FWD_NT"), *tb = getenv("BLSTM_BWD_NT"), *ev = getenv("BLSTM_REC_V");
     const int family = ev ? atoi(ev) : 0;
-    const bool want_reg = family != 2;
-    pl->tm_f = family == 3 && bl::choose_geometry_tmem(pl->H, S, pl->ndir, ctx->num_sms, cap, ef ? atoi(ef) : 0, &pl->gf);
+    const bool want_reg = family != 2, want_tmem = family == 0 || family == 3;
+    pl->tm_f = want_tmem && bl::choose_geometry_tmem(pl->H, S, pl->ndir, ctx->num_sms, cap, ef ? atoi(ef) : 0, &pl->gf);
     pl->reg_f = !pl->tm_f && want_reg && bl::choose_geometry_reg(false, pl->H, S, pl->ndir, ctx->num_sms, cap, ef ? atoi(ef) : 0, &pl->gf);
-    pl->tm_b = family == 3 && bl::choose_geometry_tmem_bwd(pl->H, S, pl->ndir, ctx->num_sms, cap, eb ? atoi(eb) : 0, &pl->gb);
+    pl->tm_b = want_tmem && bl::choose_geometry_tmem_bwd(pl->H, S, pl->ndir, ctx->num_sms, cap, eb ? atoi(eb) : 0, &pl->gb);
     pl->reg_b = !pl->tm_b && want_reg && bl::choose_geometry_reg(true, pl->H, S, pl->ndir, ctx->num_sms, cap, eb ? atoi(eb) : 0, &pl->gb);
     if ((!pl->tm_f && !pl->reg_f && !bl::choose_geometry(false, pl->H, S, pl->ndir, ctx->num_sms, cap, ef ? atoi(ef) : 0, nf ? atoi(nf) : 0, tf ? atoi(tf) : 0, &pl->gf)) ||
         (!pl->tm_b && !pl->reg_b && !bl::choose_geometry(true, pl->H, S, pl->ndir, ctx->num_sms, cap, eb ? atoi(eb) : 0, nb ? atoi(nb) : 0, tb ? atoi(tb) : 0, &pl->gb))) {

@@ -19,6 +19,7 @@
 #include <cuda_bf16.h>
 #include <cmath>
 #include <cstdint>
+#include <cstdlib>
 
 namespace bl {
 
@@ -26,6 +27,8 @@ constexpr int TM_NT = 512;
 constexpr int TM_COL_AHI = 0, TM_COL_ALO = 256, TM_COL_D = 384, TM_COLS = 512;
 
 static int tm_pad32(int x) { return (x + 31) / 32 * 32; }
+// RecGeom::K4 (unused by these kernels otherwise) carries the "merged N" switch: BLSTM_TM_MERGE=0 issues the two tf32 products separately
+static int tm_merge_default() { const char *e = getenv("BLSTM_TM_MERGE"); return (e && atoi(e) == 0) ? 0 : 1; }
 
 // RecGeom fields used: G, C, CL, SG, NT, npair, Hpad, RS (= Hpad: plain exchange rows), Spad (= NB, the MMA's N), smem
 bool choose_geometry_tmem(int H, int S, int ndir, int num_sms, int smem_cap, int forceG, RecGeom *out)
@@ -59,6 +62,7 @@ bool choose_geometry_tmem(int H, int S, int ndir, int num_sms, int smem_cap, int
             best = RecGeom{};
             best.G = G; best.C = C; best.CL = CL; best.SG = SG; best.NT = TM_NT; best.nsub = 1; best.npair = npair;
             best.R = 128; best.Hpad = Hp; best.RS = Hp; best.Spad = NB; best.smem = smem; best.cost = cost;
+            best.K4 = tm_merge_default();
         }
     }
     if (found) *out = best;
@@ -182,9 +186,14 @@ __global__ void __launch_bounds__(TM_NT, 1) lstm_fwd_tmem_kernel(const RecFwdPar
     const RecGeom &g = p.g;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int Hp = g.Hpad, NB = g.Spad;
+    // the tf32 hi and lo copies of the B operand share ONE tile of 2*NB rows (hi rows [0, NB), lo rows [NB, 2*NB)): with `merge` a
+    // single N = 2*NB MMA per k-step multiplies W_hi with both (accumulator columns [0, NB) and [NB, 2*NB), added in the epilogue) --
+    // 48 instead of 80 MMAs per C2 step; without it two N = NB MMAs address the two halves through their own descriptors
+    const bool merge = g.K4 != 0;
+    const int NB2 = 2 * NB;
     const int bhi_bytes = (Hp / 32) * NB * 128, bbf_bytes = ((Hp + 63) / 64) * NB * 128;
     uint8_t *base = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(tm_smem_raw) + 1023) & ~(uintptr_t)1023);   // SWIZZLE_128B atoms
-    uint8_t *Bhi = base, *Blo = base + bhi_bytes, *Bbf = base + 2 * bhi_bytes;
+    uint8_t *Bhl = base, *Bbf = base + 2 * bhi_bytes;
     float *stage = reinterpret_cast<float *>(base + 2 * bhi_bytes + bbf_bytes);          // [4 gates][NB][32 cells]
 
     const int H = p.H, L = p.L, S = p.S, T = p.T;
@@ -256,9 +265,9 @@ __global__ void __launch_bounds__(TM_NT, 1) lstm_fwd_tmem_kernel(const RecFwdPar
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 
-    const uint32_t idesc_tf32 = tm_make_idesc(2u, NB), idesc_bf16 = tm_make_idesc(1u, NB);
-    const uint64_t desc_hi = tm_make_desc(Bhi), desc_lo = tm_make_desc(Blo), desc_bf = tm_make_desc(Bbf);
-    const uint64_t kb_step = (uint64_t)((NB * 128) >> 4);        // next K-block of a tile, in descriptor address units
+    const uint32_t idesc_tf32 = tm_make_idesc(2u, merge ? NB2 : NB), idesc_bf16 = tm_make_idesc(1u, NB);
+    const uint64_t desc_hi = tm_make_desc(Bhl), desc_lo = desc_hi + (uint64_t)(((NB / 8) * 1024) >> 4), desc_bf = tm_make_desc(Bbf);
+    const uint64_t kb_step2 = (uint64_t)((NB2 * 128) >> 4), kb_step = (uint64_t)((NB * 128) >> 4);   // next K-block, in descriptor address units
     const int hq4 = Hp / 4;
 
     for (int q = 0; q < T; ++q) {
@@ -300,9 +309,8 @@ __global__ void __launch_bounds__(TM_NT, 1) lstm_fwd_tmem_kernel(const RecFwdPar
                 const int n = idx[u] / hq4, k = (idx[u] - n * hq4) * 4;
                 const float4 x = v[u];
                 const float4 hi = make_float4(tm_tf32(x.x), tm_tf32(x.y), tm_tf32(x.z), tm_tf32(x.w));
-                const int of = tm_off_f32(NB, n, k);
-                *reinterpret_cast<float4 *>(Bhi + of) = hi;
-                *reinterpret_cast<float4 *>(Blo + of) = make_float4(__fsub_rn(x.x, hi.x), __fsub_rn(x.y, hi.y), __fsub_rn(x.z, hi.z), __fsub_rn(x.w, hi.w));
+                *reinterpret_cast<float4 *>(Bhl + tm_off_f32(NB2, n, k)) = hi;
+                *reinterpret_cast<float4 *>(Bhl + tm_off_f32(NB2, NB + n, k)) = make_float4(__fsub_rn(x.x, hi.x), __fsub_rn(x.y, hi.y), __fsub_rn(x.z, hi.z), __fsub_rn(x.w, hi.w));
                 uint2 b; b.x = tm_bf16(x.x) | (tm_bf16(x.y) << 16); b.y = tm_bf16(x.z) | (tm_bf16(x.w) << 16);
                 *reinterpret_cast<uint2 *>(Bbf + tm_off_bf16(NB, n, k)) = b;
             }
@@ -313,15 +321,20 @@ __global__ void __launch_bounds__(TM_NT, 1) lstm_fwd_tmem_kernel(const RecFwdPar
             if (warp == 4) {
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 if (tm_elect_one()) {
-                    uint32_t acc = 0u;                         // small terms first, then the leading one
-                    for (int ks = 0; ks < Hp / 16; ++ks) {     // bf16: 16 k per MMA = 8 TMEM columns = 32 B inside the swizzle atom
-                        tm_mma_bf16(tmem + TM_COL_D, tmem + TM_COL_ALO + ks * 8, desc_bf + (uint64_t)(ks >> 2) * kb_step + (uint64_t)((ks & 3) * 2), idesc_bf16, acc);
-                        acc = 1u;
+                    // tf32: 8 k per MMA = 8 TMEM columns = 32 B inside the swizzle atom; bf16: 16 k per MMA, likewise 8 columns / 32 B
+                    if (merge) {
+                        for (int ks = 0; ks < Hp / 8; ++ks)
+                            tm_mma_tf32(tmem + TM_COL_D, tmem + TM_COL_AHI + ks * 8, desc_hi + (uint64_t)(ks >> 2) * kb_step2 + (uint64_t)((ks & 3) * 2), idesc_tf32, ks ? 1u : 0u);
+                        for (int ks = 0; ks < Hp / 16; ++ks)
+                            tm_mma_bf16(tmem + TM_COL_D, tmem + TM_COL_ALO + ks * 8, desc_bf + (uint64_t)(ks >> 2) * kb_step + (uint64_t)((ks & 3) * 2), idesc_bf16, 1u);
+                    } else {                                   // small terms first, then the leading one
+                        for (int ks = 0; ks < Hp / 16; ++ks)
+                            tm_mma_bf16(tmem + TM_COL_D, tmem + TM_COL_ALO + ks * 8, desc_bf + (uint64_t)(ks >> 2) * kb_step + (uint64_t)((ks & 3) * 2), idesc_bf16, ks ? 1u : 0u);
+                        for (int ks = 0; ks < Hp / 8; ++ks)
+                            tm_mma_tf32(tmem + TM_COL_D, tmem + TM_COL_AHI + ks * 8, desc_lo + (uint64_t)(ks >> 2) * kb_step2 + (uint64_t)((ks & 3) * 2), idesc_tf32, 1u);
+                        for (int ks = 0; ks < Hp / 8; ++ks)
+                            tm_mma_tf32(tmem + TM_COL_D, tmem + TM_COL_AHI + ks * 8, desc_hi + (uint64_t)(ks >> 2) * kb_step2 + (uint64_t)((ks & 3) * 2), idesc_tf32, 1u);
                     }
-                    for (int ks = 0; ks < Hp / 8; ++ks)        // tf32: 8 k per MMA = 8 TMEM columns = 32 B inside the swizzle atom
-                        tm_mma_tf32(tmem + TM_COL_D, tmem + TM_COL_AHI + ks * 8, desc_lo + (uint64_t)(ks >> 2) * kb_step + (uint64_t)((ks & 3) * 2), idesc_tf32, 1u);
-                    for (int ks = 0; ks < Hp / 8; ++ks)
-                        tm_mma_tf32(tmem + TM_COL_D, tmem + TM_COL_AHI + ks * 8, desc_hi + (uint64_t)(ks >> 2) * kb_step + (uint64_t)((ks & 3) * 2), idesc_tf32, 1u);
                     tm_commit(&s_bar);
                 }
                 __syncwarp();
@@ -332,6 +345,12 @@ __global__ void __launch_bounds__(TM_NT, 1) lstm_fwd_tmem_kernel(const RecFwdPar
                 for (int c = 0; c < NB; c += 16) {
                     float dv[16];
                     tm_ld16(tmem + ((uint32_t)(warp * 32) << 16) + TM_COL_D + c, dv);
+                    if (merge) {
+                        float dl[16];
+                        tm_ld16(tmem + ((uint32_t)(warp * 32) << 16) + TM_COL_D + NB + c, dl);
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) dv[i] = __fadd_rn(dv[i], dl[i]);
+                    }
 #pragma unroll
                     for (int i = 0; i < 16; ++i) stage[(warp * NB + c + i) * 32 + lane] = dv[i];
                 }
@@ -442,6 +461,7 @@ bool choose_geometry_tmem_bwd(int H, int S, int ndir, int num_sms, int smem_cap,
             best = RecGeom{};
             best.G = G; best.C = C; best.CL = CL; best.SG = SG; best.NT = TM_NT; best.nsub = 1; best.npair = npair;
             best.R = R; best.Hpad = R; best.Spad = NB; best.smem = smem; best.cost = cost;
+            best.K4 = tm_merge_default();
             // the plan allocates ndir*2*S*RS floats for the exchange buffer: make that cover [G][C][NB][R] per (dir, parity)
             best.RS = (int)(((size_t)G * C * NB * R + S - 1) / S);
         }
@@ -460,9 +480,11 @@ __global__ void __launch_bounds__(TM_NT, 1) lstm_bwd_tmem_kernel(const RecBwdPar
     const RecGeom &g = p.g;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int R = g.Hpad, MT = R / 128, NB = g.Spad;
+    const bool merge = g.K4 != 0;                                          // one N = 2*NB MMA for W_hi*(d_hi | d_lo), see the forward kernel
+    const int NB2 = 2 * NB;
     const int bhi_bytes = 4 * NB * 128, bbf_bytes = 2 * NB * 128;          // K = 128: 4 K-blocks of 32 floats, 2 of 64 bf16
     uint8_t *base = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(tm_smem_raw) + 1023) & ~(uintptr_t)1023);
-    uint8_t *Bhi = base, *Blo = base + bhi_bytes, *Bbf = base + 2 * bhi_bytes;
+    uint8_t *Bhl = base, *Bbf = base + 2 * bhi_bytes;                      // hi rows [0, NB), lo rows [NB, 2*NB) of one tile
 
     const int H = p.H, L = p.L, S = p.S, T = p.T;
     const int d = blockIdx.x / (g.G * g.C);
@@ -539,9 +561,10 @@ __global__ void __launch_bounds__(TM_NT, 1) lstm_bwd_tmem_kernel(const RecBwdPar
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 
-    const uint32_t idesc_tf32 = tm_make_idesc(2u, NB), idesc_bf16 = tm_make_idesc(1u, NB);
-    const uint64_t desc_hi = tm_make_desc(Bhi), desc_lo = tm_make_desc(Blo), desc_bf = tm_make_desc(Bbf);
-    const uint64_t kb_step = (uint64_t)((NB * 128) >> 4);
+    const uint32_t idesc_tf32 = tm_make_idesc(2u, merge ? NB2 : NB), idesc_bf16 = tm_make_idesc(1u, NB);
+    const uint64_t desc_hi = tm_make_desc(Bhl), desc_lo = desc_hi + (uint64_t)(((NB / 8) * 1024) >> 4), desc_bf = tm_make_desc(Bbf);
+    const uint64_t kb_step2 = (uint64_t)((NB2 * 128) >> 4), kb_step = (uint64_t)((NB * 128) >> 4);
+    const int dstride = merge ? NB2 : NB;                        // accumulator columns per 128-row tile
     const size_t ex_slice = (size_t)NB * R;                      // one producer's [NB][R] block
 
     for (int q = 0; q < T; ++q) {
@@ -622,9 +645,8 @@ __global__ void __launch_bounds__(TM_NT, 1) lstm_bwd_tmem_kernel(const RecBwdPar
 #pragma unroll
                 for (int gi = 0; gi < 4; ++gi) {
                     const float hi = tm_tf32(dv[gi]);
-                    const int of = tm_off_f32(NB, sl_[u], gi * 32 + cl);
-                    *reinterpret_cast<float *>(Bhi + of) = hi;
-                    *reinterpret_cast<float *>(Blo + of) = __fsub_rn(dv[gi], hi);
+                    *reinterpret_cast<float *>(Bhl + tm_off_f32(NB2, sl_[u], gi * 32 + cl)) = hi;
+                    *reinterpret_cast<float *>(Bhl + tm_off_f32(NB2, NB + sl_[u], gi * 32 + cl)) = __fsub_rn(dv[gi], hi);
                     *reinterpret_cast<unsigned short *>(Bbf + tm_off_bf16(NB, sl_[u], gi * 32 + cl)) = (unsigned short)tm_bf16(dv[gi]);
                 }
             }
@@ -636,17 +658,21 @@ __global__ void __launch_bounds__(TM_NT, 1) lstm_bwd_tmem_kernel(const RecBwdPar
             if (warp == 4) {
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 if (tm_elect_one()) {
-                    for (int mt = 0; mt < MT; ++mt) {
-                        const uint32_t dcol = tmem + TM_COL_D + mt * NB;
-                        uint32_t acc = 0u;                     // small terms first, then the leading one
-                        for (int ks = 0; ks < 8; ++ks) {       // bf16: K = 128 = 8 MMAs of 16
-                            tm_mma_bf16(dcol, tmem + TM_COL_ALO + mt * 64 + ks * 8, desc_bf + (uint64_t)(ks >> 2) * kb_step + (uint64_t)((ks & 3) * 2), idesc_bf16, acc);
-                            acc = 1u;
+                    for (int mt = 0; mt < MT; ++mt) {          // tf32: K = 128 = 16 MMAs of 8; bf16: 8 MMAs of 16
+                        const uint32_t dcol = tmem + TM_COL_D + mt * dstride;
+                        if (merge) {
+                            for (int ks = 0; ks < 16; ++ks)
+                                tm_mma_tf32(dcol, tmem + TM_COL_AHI + mt * 128 + ks * 8, desc_hi + (uint64_t)(ks >> 2) * kb_step2 + (uint64_t)((ks & 3) * 2), idesc_tf32, ks ? 1u : 0u);
+                            for (int ks = 0; ks < 8; ++ks)
+                                tm_mma_bf16(dcol, tmem + TM_COL_ALO + mt * 64 + ks * 8, desc_bf + (uint64_t)(ks >> 2) * kb_step + (uint64_t)((ks & 3) * 2), idesc_bf16, 1u);
+                        } else {                               // small terms first, then the leading one
+                            for (int ks = 0; ks < 8; ++ks)
+                                tm_mma_bf16(dcol, tmem + TM_COL_ALO + mt * 64 + ks * 8, desc_bf + (uint64_t)(ks >> 2) * kb_step + (uint64_t)((ks & 3) * 2), idesc_bf16, ks ? 1u : 0u);
+                            for (int ks = 0; ks < 16; ++ks)
+                                tm_mma_tf32(dcol, tmem + TM_COL_AHI + mt * 128 + ks * 8, desc_lo + (uint64_t)(ks >> 2) * kb_step2 + (uint64_t)((ks & 3) * 2), idesc_tf32, 1u);
+                            for (int ks = 0; ks < 16; ++ks)
+                                tm_mma_tf32(dcol, tmem + TM_COL_AHI + mt * 128 + ks * 8, desc_hi + (uint64_t)(ks >> 2) * kb_step2 + (uint64_t)((ks & 3) * 2), idesc_tf32, 1u);
                         }
-                        for (int ks = 0; ks < 16; ++ks)        // tf32: K = 128 = 16 MMAs of 8
-                            tm_mma_tf32(dcol, tmem + TM_COL_AHI + mt * 128 + ks * 8, desc_lo + (uint64_t)(ks >> 2) * kb_step + (uint64_t)((ks & 3) * 2), idesc_tf32, 1u);
-                        for (int ks = 0; ks < 16; ++ks)
-                            tm_mma_tf32(dcol, tmem + TM_COL_AHI + mt * 128 + ks * 8, desc_hi + (uint64_t)(ks >> 2) * kb_step + (uint64_t)((ks & 3) * 2), idesc_tf32, 1u);
                     }
                     tm_commit(&s_bar);
                 }
@@ -658,7 +684,13 @@ __global__ void __launch_bounds__(TM_NT, 1) lstm_bwd_tmem_kernel(const RecBwdPar
                 for (int mt = 0; mt < MT; ++mt)
                     for (int cc = 0; cc < NB; cc += 16) {
                         float dv[16];
-                        tm_ld16(tmem + ((uint32_t)(warp * 32) << 16) + TM_COL_D + mt * NB + cc, dv);
+                        tm_ld16(tmem + ((uint32_t)(warp * 32) << 16) + TM_COL_D + mt * dstride + cc, dv);
+                        if (merge) {
+                            float dl[16];
+                            tm_ld16(tmem + ((uint32_t)(warp * 32) << 16) + TM_COL_D + mt * dstride + NB + cc, dl);
+#pragma unroll
+                            for (int i = 0; i < 16; ++i) dv[i] = __fadd_rn(dv[i], dl[i]);
+                        }
 #pragma unroll
                         for (int i = 0; i < 16; ++i)
                             if (cc + i < nseq) ex_w[(size_t)(cc + i) * R + mt * 128 + warp * 32 + lane] = dv[i];

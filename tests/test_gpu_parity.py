@@ -167,9 +167,12 @@ def test_network_forward_backward_parity(oracle, gpu_ctx, case):
     print(name, "worst rel err %.2e" % worst)
 
 
+@pytest.mark.parametrize("family", ["tmem", "registers"])
 @pytest.mark.parametrize("G", [1, 2, 3])
-def test_sequence_group_geometries(oracle, gpu_ctx, G, monkeypatch):
+def test_sequence_group_geometries(oracle, gpu_ctx, G, family, monkeypatch):
     """The persistent kernels must give the same result for every (sequence groups x cell slices) decomposition."""
+    if family == "registers":
+        monkeypatch.setenv("BLSTM_REC_V", "1")
     monkeypatch.setenv("BLSTM_FWD_G", str(G))
     monkeypatch.setenv("BLSTM_BWD_G", str(G))
     net_json = synth.network_json(11, [34, ("lstm", 21)], 9)
@@ -179,14 +182,11 @@ def test_sequence_group_geometries(oracle, gpu_ctx, G, monkeypatch):
 
 @pytest.mark.parametrize("family", ["registers", "smem", "tmem"])
 def test_both_recurrent_kernel_families(oracle, gpu_ctx, family, monkeypatch):
-    """Register-resident (default), shared-memory-resident (BLSTM_REC_V=2, the fallback for slices that do not fit the
-    register file) and tensor-memory-resident (BLSTM_REC_V=3: forward step GEMM on tcgen05 with the weights in TMEM) kernels
-    implement the same step protocol and must all hold the parity bar."""
+    """Tensor-memory-resident (default where the slice fits: step GEMM on tcgen05 with the weights in TMEM), register-resident
+    (BLSTM_REC_V=1; the default for wider layers) and shared-memory-resident (BLSTM_REC_V=2, the fallback for slices that do not
+    fit the register file) kernels implement the same step protocol and must all hold the parity bar."""
     import currennt_b200 as cb
-    if family == "smem":
-        monkeypatch.setenv("BLSTM_REC_V", "2")
-    if family == "tmem":
-        monkeypatch.setenv("BLSTM_REC_V", "3")
+    monkeypatch.setenv("BLSTM_REC_V", {"registers": "1", "smem": "2", "tmem": "3"}[family])
     net_json = synth.network_json(13, [48, ("lstm", 27)], 11)
     info = cb.Net(gpu_ctx, net_json, 6, 16).plan_info(1)
     assert info["fwd_kernel"] == family and info["bwd_kernel"] == family, info
@@ -212,7 +212,8 @@ def test_tensor_memory_recurrent_kernels(oracle, gpu_ctx, case, monkeypatch):
     sequence groups."""
     import currennt_b200 as cb
     name, net_json, S, lengths, classes, G = case
-    monkeypatch.setenv("BLSTM_REC_V", "3")
+    if name.startswith("one_group"):           # also without the merged-N MMA (two tf32 products issued separately)
+        monkeypatch.setenv("BLSTM_TM_MERGE", "0")
     if G:
         monkeypatch.setenv("BLSTM_FWD_G", str(G))
         monkeypatch.setenv("BLSTM_BWD_G", str(G))
@@ -223,9 +224,8 @@ def test_tensor_memory_recurrent_kernels(oracle, gpu_ctx, case, monkeypatch):
 
 
 def test_tensor_memory_kernel_falls_back_when_weights_do_not_fit(gpu_ctx, monkeypatch):
-    """pad32(H) > 256 does not fit the 512 TMEM columns: BLSTM_REC_V=3 then keeps the register / shared-memory kernels."""
+    """pad32(H) > 256 does not fit the 512 TMEM columns: such layers keep the register / shared-memory kernels."""
     import currennt_b200 as cb
-    monkeypatch.setenv("BLSTM_REC_V", "3")
     info = cb.Net(gpu_ctx, synth.network_json(9, [("lstm", 300)], 4), 2, 6).plan_info(1)
     assert info["fwd_kernel"] != "tmem" and info["bwd_kernel"] != "tmem", info
 
@@ -443,13 +443,13 @@ def _full_net(gpu_ctx, name, S, maxT):
     return cfg, net, weights
 
 
-@pytest.mark.parametrize("family", ["default", "tmem"])
+@pytest.mark.parametrize("family", ["tmem", "registers"])
 def test_c2_network_against_oracle_short_sequences(oracle, gpu_ctx, family, monkeypatch):
     """The full TIMIT-shape network (123 -> 3 x blstm 500 -> softmax 183, S=100) against the oracle on a fraction short enough
     for the CPU oracle (T=10): every tensor within the strict bar.  Exercises the production geometry (G=9 x C=8 slices,
     register-resident weights) and the tcgen05 GEMMs at their real M/N."""
-    if family == "tmem":                       # forward step GEMM on tcgen05, weights in tensor memory (G=9 x C=8, N=16, K=256)
-        monkeypatch.setenv("BLSTM_REC_V", "3")
+    if family == "registers":                  # default: step GEMMs on tcgen05, weights in tensor memory (G=9 x C=8, N=16, K=256)
+        monkeypatch.setenv("BLSTM_REC_V", "1")
     cfg = synth.config("C2")
     rng = np.random.default_rng(3)
     lengths = sorted(rng.integers(6, 11, 100).tolist())

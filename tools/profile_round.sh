@@ -12,9 +12,9 @@ timeout 400 python bench.py 2>$OUT/${TAG}_bench.err | tail -1 > $OUT/${TAG}_benc
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 3000 --csv --log-file $OUT/${TAG}_launches.csv \
     python bench.py --steps 2 --warmup 3 > $OUT/${TAG}_launches.log 2>&1
 # 3. one full capture of each top kernel
-timeout 400 ncu --set full --clock-control none --import-source on -k regex:lstm_fwd_reg -s 4 -c 1 -f -o $OUT/${TAG}_fwd_full \
+timeout 400 ncu --set full --clock-control none --import-source on -k regex:lstm_fwd_ -s 4 -c 1 -f -o $OUT/${TAG}_fwd_full \
     python bench.py --steps 1 --warmup 3 > $OUT/${TAG}_ncu_fwd.log 2>&1
-timeout 400 ncu --set full --clock-control none --import-source on -k regex:lstm_bwd_reg -s 4 -c 1 -f -o $OUT/${TAG}_bwd_full \
+timeout 400 ncu --set full --clock-control none --import-source on -k regex:lstm_bwd_ -s 4 -c 1 -f -o $OUT/${TAG}_bwd_full \
     python bench.py --steps 1 --warmup 3 > $OUT/${TAG}_ncu_bwd.log 2>&1
 timeout 400 ncu --set full --clock-control none --import-source on -k regex:2cta -s 40 -c 13 -f -o $OUT/${TAG}_gemm_full \
     python bench.py --steps 1 --warmup 3 > $OUT/${TAG}_ncu_gemm.log 2>&1
