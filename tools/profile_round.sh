@@ -16,8 +16,11 @@ timeout 400 ncu --set full --clock-control none --import-source on -k regex:lstm
     python bench.py --steps 1 --warmup 3 > $OUT/${TAG}_ncu_fwd.log 2>&1
 timeout 400 ncu --set full --clock-control none --import-source on -k regex:lstm_bwd_ -s 4 -c 1 -f -o $OUT/${TAG}_bwd_full \
     python bench.py --steps 1 --warmup 3 > $OUT/${TAG}_ncu_bwd.log 2>&1
+# (PROFILE_GEMM=0 skips the GEMM capture when those kernels have not changed since the committed summary)
+if [ "${PROFILE_GEMM:-1}" = "1" ]; then
 timeout 400 ncu --set full --clock-control none --import-source on -k regex:2cta -s 40 -c 13 -f -o $OUT/${TAG}_gemm_full \
     python bench.py --steps 1 --warmup 3 > $OUT/${TAG}_ncu_gemm.log 2>&1
+fi
 # 4. in-kernel phase trace of the forward recurrent kernel (one C2 layer, T=300)
 BLSTM_REC_TRACE=1 timeout 300 python tools/trace_recurrent.py 250 100 300 > $OUT/${TAG}_recurrent_trace.txt 2>&1
 ls -la $OUT | tail -20
