@@ -1,7 +1,7 @@
 """Generates tests/golden/*.npz from the REFERENCE ITSELF: the unmodified CURRENNT CPU objects compiled by
 oracle/build_ref.sh from /root/reference (oracle/_ref/libcurrennt_ref.so).  Run in the build container:
 
-    python tests/golden/make_golden.py
+    python tests/golden/make_golden.py [--all]        # without --all only missing fixtures are written
 
 Each file holds the network JSON, the per-layer initial weights, one packed fraction, and what the reference
 computed for it: every layer's outputs / outputErrors / weightUpdates, the objective and (multiclass) the number of
@@ -30,12 +30,19 @@ CASES = {
     "softmax_ce": (synth.network_json(6, [10], 5, "softmax", "ce"), 3, [3, 4, 6], 0, 5, 25),
     "mixed_ff": (synth.network_json(9, [("blstm", 8), ("feedforward_tanh", 5), ("lstm", 6), ("feedforward_logistic", 4), ("blstm", 10)], 6),
                  5, [1, 4, 7, 7, 9], 6, 0, 26),
+    # the remaining objectives of LayerFactory.cu:66-81
+    "rmse_identity": (synth.network_json(7, [10], 5, "feedforward_identity", "rmse"), 4, [2, 5, 7, 7], 0, 5, 27),
+    "weightedsse_tanh": (synth.network_json(6, [8], 4, "feedforward_tanh", "weightedsse"), 3, [3, 5, 6], 0, 8, 28),
+    "wf_mask_lstm": (synth.network_json(6, [("lstm", 7)], 4, "feedforward_logistic", "wf"), 3, [1, 5, 6], 0, 8, 29),
+    "binary_logistic": (synth.network_json(8, [10], 1, "feedforward_logistic", "binary_classification"), 5, [1, 4, 6, 6], 2, 0, 30),
 }
 
 
 def main():
     pyoracle.build(ref=True)
     for name, (net_json, S, lengths, classes, tsize, seed) in CASES.items():
+        if os.path.exists(os.path.join(HERE, name + ".npz")) and "--all" not in sys.argv:
+            continue                                   # committed fixtures are only rewritten on request
         weights, frac = small_case(pyoracle, net_json, S, lengths, seed, classes=classes, target_size=tsize)
         if name == "softmax_ce":
             t = np.abs(frac.targets) + 0.1

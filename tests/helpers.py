@@ -67,7 +67,8 @@ def load_golden(name):
     return np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", name + ".npz"))
 
 
-GOLDEN = ["blstm_softmax_ragged", "lstm_softmax", "test1_shape", "autoencoder_sse", "softmax_ce", "mixed_ff"]
+GOLDEN = ["blstm_softmax_ragged", "lstm_softmax", "test1_shape", "autoencoder_sse", "softmax_ce", "mixed_ff",
+          "rmse_identity", "weightedsse_tanh", "wf_mask_lstm", "binary_logistic"]
 
 
 def replay_golden(net_cls_factory, name):
