@@ -159,6 +159,79 @@ def test_cli_forward_pass_single_csv(oracle, tmp_path):
             k += 1
 
 
+def _oracle_train_epochs(oracle, net_json, xs, cs, ts, weights, S, lr, mom, epochs):
+    """Training epochs of any task (class targets cs or dense targets ts) replayed by the oracle: per-epoch (error / #sequences,
+    #correct or None), and the network."""
+    order = np.argsort([len(x) for x in xs], kind="stable")
+    xs = [xs[i] for i in order]
+    cs = None if cs is None else [cs[i] for i in order]
+    ts = None if ts is None else [ts[i] for i in order]
+    O = json.loads(net_json)["layers"][-1]["size"]
+    net = oracle.OracleNet(net_json, S, max(len(x) for x in xs))
+    for i, w in enumerate(weights):
+        if len(w):
+            net.set_weights(i, w)
+    deltas = [np.zeros_like(w) for w in weights]
+    rows = []
+    for _ in range(epochs):
+        e = c = 0
+        for first in range(0, len(xs), S):
+            f = oracle.make_fraction(xs, S, first, seq_classes=cs, seq_targets=ts, O=O)
+            net.load_fraction(f); net.forward(); e += net.calculate_error()
+            if cs is not None:
+                c += net.count_correct()
+            net.backward()
+            net.sgd_update(deltas, lr, mom)
+        rows.append((e / len(xs), c if cs is not None else None))
+    return net, rows
+
+
+def test_cli_binary_classification_task(oracle, tmp_path):
+    """A two-label data set gives an output pattern size of 1 (DataSet.cpp:104-107) and trains a logistic output under
+    binary_classification (BinaryClassificationLayer.cu); the table shows classification error and objective like the reference."""
+    net_json = synth.network_json(11, [16], 1, "feedforward_logistic", "binary_classification")
+    lens = np.random.default_rng(8).permutation(np.arange(6, 26))
+    xs, cs, _ = synth.make_sequences(lens, 11, 3, classes=2)
+    weights = synth.init_weights(net_json, 4)
+    write_nc(str(tmp_path / "train.nc"), xs, cs, labels=2)
+    json.dump(_with_weights(net_json, weights), open(tmp_path / "network.jsn", "w"))
+    out = _run(["--network", "network.jsn", "--train", "true", "--train_file", "train.nc", "--stochastic", "true", "--parallel_sequences", "5",
+                "--learning_rate", "1e-3", "--momentum", "0.9", "--max_epochs", "2", "--save_network", "trained.jsn"], str(tmp_path))
+    rows = _epoch_rows(out)
+    net, want = _oracle_train_epochs(oracle, net_json, xs, cs, None, weights, 5, 1e-3, 0.9, 2)
+    assert len(rows) == 2
+    frames = int(lens.sum())
+    for got, (err, correct) in zip(rows, want):
+        assert abs(got[1] - 100.0 * (1.0 - correct / frames)) <= 0.011 and abs(got[2] - err) <= 0.0011
+    doc, saved = _saved_weights(tmp_path / "trained.jsn")
+    assert doc["layers"][-1]["type"] == "binary_classification"
+    for i, layer in enumerate(doc["layers"]):
+        if layer["name"] in saved:
+            assert rel_err(saved[layer["name"]], net.get_weights(i)) <= 1e-5
+
+
+def test_cli_regression_task_rmse(oracle, tmp_path):
+    """Dense targets (targetPatterns) with the rmse objective: the table has one error column per set (main.cpp:216), and the
+    trained weights follow the oracle."""
+    net_json = synth.network_json(9, [("lstm", 12)], 5, "feedforward_identity", "rmse")
+    lens = np.random.default_rng(9).permutation(np.arange(5, 21))
+    xs, _, ts = synth.make_sequences(lens, 9, 5, target_size=5)
+    weights = synth.init_weights(net_json, 6)
+    write_nc(str(tmp_path / "train.nc"), xs, ts=ts)
+    json.dump(_with_weights(net_json, weights), open(tmp_path / "network.jsn", "w"))
+    out = _run(["--network", "network.jsn", "--train", "true", "--train_file", "train.nc", "--stochastic", "true", "--parallel_sequences", "4",
+                "--learning_rate", "1e-3", "--momentum", "0.9", "--max_epochs", "2", "--save_network", "trained.jsn"], str(tmp_path))
+    rows = [(int(m.group(1)), float(m.group(2))) for m in re.finditer(r"^\s+(\d+) \|\s+[\d.]+ \|\s+([\d.]+) \|", out, re.M)]
+    net, want = _oracle_train_epochs(oracle, net_json, xs, None, ts, weights, 4, 1e-3, 0.9, 2)
+    assert [r[0] for r in rows] == [1, 2]
+    for got, (err, _) in zip(rows, want):
+        assert abs(got[1] - err) <= 0.0011                                           # %17.3lf
+    doc, saved = _saved_weights(tmp_path / "trained.jsn")
+    for i, layer in enumerate(doc["layers"]):
+        if layer["name"] in saved:
+            assert rel_err(saved[layer["name"]], net.get_weights(i)) <= 1e-5
+
+
 def test_cli_rejects_what_it_does_not_implement(tmp_path):
     r = subprocess.run([EXE, "--cuda", "false"], capture_output=True, text=True)
     assert r.returncode == 2 and "no CPU path" in r.stdout
