@@ -109,18 +109,27 @@ def algorithmic_work(net_json, slots):
 
 
 # ------------------------------------------------------------------------------------------- reference arm / cpu baseline
-def cpu_reference_rate(steps, warmup, S=8, T=40, seed=2):
-    """The reference's own CPU path (NeuralNetwork<Cpu>, --cuda false) on a bounded sample of the C2 workload."""
+def cpu_reference_rate(steps, warmup, S=8, T=40, seed=2, threads=1):
+    """The reference's own CPU path (NeuralNetwork<Cpu>, --cuda false) on a bounded sample of the C2 workload.
+    threads == 1: the reference as its own build makes it (sequential host Thrust).  threads > 1: the same sources built with
+    Thrust's OpenMP host backend (oracle/_ref/libcurrennt_ref_omp.so) -- every host thread the reference can be given."""
     from oracle import pyoracle
     cfg = synth.config("C2")
     net_json = cfg["net"]
+    omp = threads > 1 and pyoracle.ref_omp_available()
+    if not omp:
+        threads = 1
     kind = "reference" if pyoracle.ref_available() else "port"
     rng = np.random.default_rng(seed)
     lengths = np.clip(np.round(rng.lognormal(np.log(0.8 * T), 0.25, S)), 4, T).astype(int)
     lengths[-1] = T
     xs, cs, _ = synth.make_sequences(lengths, 123, seed, classes=183)
     frac = pyoracle.make_fraction(xs, S, 0, seq_classes=cs, O=183)
-    net = (pyoracle.RefNet if kind == "reference" else pyoracle.OracleNet)(net_json, S, T)
+    if omp:
+        pyoracle.set_omp_threads(threads)
+        net = pyoracle.RefNet(net_json, S, T, omp=True)
+    else:
+        net = (pyoracle.RefNet if kind == "reference" else pyoracle.OracleNet)(net_json, S, T)
     for i, w in enumerate(synth.init_weights(net_json, seed + 1)):
         if len(w):
             net.set_weights(i, w)
@@ -136,20 +145,41 @@ def cpu_reference_rate(steps, warmup, S=8, T=40, seed=2):
             times.append(time.perf_counter() - t0)
     total = sum(times)
     sample = ("C2 network, one fraction S=%d T=%d (%d valid frames of %d slots), %d passes of loadSequences+forward+error+backward "
-              "(SGD update excluded: 3.85M weights, <1%% of the step)" % (S, T, frac.valid_frames, frac.N, steps))
-    return {"value": frac.valid_frames * steps / total, "unit": UNIT, "cores": 1, "kind": kind, "sample": sample,
+              "(SGD update excluded: 3.85M weights, <1%% of the step); %s" %
+              (S, T, frac.valid_frames, frac.N, steps,
+               "Thrust OpenMP host backend build of the unmodified sources, %d threads" % threads if omp
+               else "the reference's own build configuration: sequential host Thrust, 1 thread"))
+    return {"value": frac.valid_frames * steps / total, "unit": UNIT, "cores": threads, "kind": kind, "sample": sample,
             "ms_per_step": 1e3 * total / steps, "frames_per_step": frac.valid_frames}
+
+
+def cpu_reference_best(steps, warmup):
+    """The reference with all the host threads it can use: the OpenMP build at the best of a few thread counts (one probe pass
+    each), next to the single-threaded configuration its own CMakeLists produces.  Returns (best, single_thread)."""
+    from oracle import pyoracle
+    single = cpu_reference_rate(min(steps, 4), 1)
+    if not pyoracle.ref_omp_available():
+        return single, single
+    ncpu = os.cpu_count() or 1
+    cands = sorted({n for n in (ncpu, ncpu // 2, 64, 32, 16, 8) if 1 < n <= ncpu})
+    if not cands:
+        return single, single
+    probe = {n: cpu_reference_rate(1, 1, threads=n)["value"] for n in cands}
+    best_n = max(probe, key=probe.get)
+    best = cpu_reference_rate(steps, warmup, threads=best_n)
+    return (best if best["value"] > single["value"] else single), single
 
 
 def run_reference(args, rank):
     if rank != 0:
         return
     steps = args.steps
-    base = cpu_reference_rate(steps, max(1, min(args.warmup, 2)))
+    base, single = cpu_reference_best(steps, max(1, min(args.warmup, 2)))
     line = {"impl": "reference", "metric": METRIC, "value": base["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
             "warmup": args.warmup, "ms_per_step": base["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic", "config": {"workload": WORKLOAD["C2"], "reference_sample": base["sample"]},
             "cpu_baseline": {k: base[k] for k in ("value", "unit", "cores", "kind", "sample")},
+            "single_thread": {k: single[k] for k in ("value", "unit", "cores", "sample")},
             "e2e": {"value": base["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
     print(json.dumps(line), flush=True)
 
@@ -310,7 +340,7 @@ def run_ours(args, rank, world, local_rank):
                     "algorithmic_bytes_per_launch": (fwd_b + bwd_b) / max(n_launch, 1), "avg_launch_ms": rec_ms / max(n_launch, 1),
                     "share_of_kernel_time": share[1] + share[2]}
         h2d = sum(f.N * (123 * 4 + 4) for f in timed) / K + sum(f.N for f in timed) / K * len(layer_shapes(net_json))
-        base = cpu_reference_rate(4, 1) if world == 1 else None
+        base, single = cpu_reference_best(4, 1) if world == 1 else (None, None)
         line = {"metric": METRIC, "value": total_frames / (dev_ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
                 "ms_per_step": e2e_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
                 "data": "synthetic",
@@ -323,6 +353,7 @@ def run_ours(args, rank, world, local_rank):
                 "kernel_classes": classes}
         if base:
             line["cpu_baseline"] = {kk: base[kk] for kk in ("value", "unit", "cores", "kind", "sample")}
+            line["cpu_baseline"]["single_thread_value"] = single["value"]
         print(json.dumps(line), flush=True)
 
     if comm is not None:

@@ -22,7 +22,10 @@ set -euo pipefail
 HERE="$(cd "$(dirname "${BASH_SOURCE[0]}")" && pwd)"
 REF="${CURRENNT_REFERENCE:-/root/reference}"
 OUT="$HERE/_ref"
-LIB="$OUT/libcurrennt_ref.so"
+# REF_VARIANT=omp builds the same sources with Thrust's OpenMP host backend (all host cores; timing baseline only -- its parallel
+# reductions sum in a different order, so parity always uses the default sequential build)
+VARIANT="${REF_VARIANT:-}"
+LIB="$OUT/libcurrennt_ref${VARIANT:+_$VARIANT}.so"
 
 if [ ! -d "$REF/currennt_lib/src" ]; then
     if [ -f "$LIB" ]; then echo "[build_ref] $REF absent; keeping prebuilt $LIB"; exit 0; fi
@@ -57,6 +60,11 @@ SRCS=(
 
 FLAGS=(-x cu -O3 -Xcompiler -O3,-fPIC -std=c++17 -arch=sm_100a -w
        -include thrust/transform_reduce.h -I "$HERE/boost_shim" -I "$WORK/src")
+LINK=()
+if [ "$VARIANT" = "omp" ]; then
+    FLAGS+=(-DTHRUST_HOST_SYSTEM=THRUST_HOST_SYSTEM_OMP -Xcompiler -fopenmp)
+    LINK=(-Xcompiler -fopenmp)
+fi
 
 pids=()
 for s in "${SRCS[@]}"; do
@@ -73,5 +81,5 @@ done
 pids+=($!)
 for p in "${pids[@]}"; do wait "$p"; done
 
-"$NVCC" -shared -Xlinker -Bsymbolic -arch=sm_100a -o "$LIB" "$WORK"/obj/*.o -lcublas
+"$NVCC" -shared -Xlinker -Bsymbolic -arch=sm_100a "${LINK[@]}" -o "$LIB" "$WORK"/obj/*.o -lcublas
 echo "[build_ref] built $LIB"

@@ -337,16 +337,29 @@ class OracleNet:
 
 # --------------------------------------------------------------------------- the reference itself
 _ref = None
+_ref_omp = None
+# the same sources built with Thrust's OpenMP host backend (REF_VARIANT=omp oracle/build_ref.sh): a TIMING baseline on all host
+# cores only -- its parallel reductions sum in a different order, parity always uses the sequential build
+REF_OMP_SO = os.path.join(HERE, "_ref", "libcurrennt_ref_omp.so")
 
 
 def ref_available():
     return os.path.exists(REF_SO)
 
 
-def ref_lib():
-    global _ref
-    if _ref is None:
-        L = ctypes.CDLL(REF_SO, mode=ctypes.RTLD_LOCAL)
+def ref_omp_available():
+    return os.path.exists(REF_OMP_SO)
+
+
+def set_omp_threads(n):
+    """Thread count of the OpenMP build (overrides OMP_NUM_THREADS, which torchrun sets to 1)."""
+    ctypes.CDLL("libgomp.so.1", mode=ctypes.RTLD_GLOBAL).omp_set_num_threads(int(n))
+
+
+def ref_lib(omp=False):
+    global _ref, _ref_omp
+    if (_ref_omp if omp else _ref) is None:
+        L = ctypes.CDLL(REF_OMP_SO if omp else REF_SO, mode=ctypes.RTLD_LOCAL)
         vp, ci, cl = ctypes.c_void_p, ctypes.c_int, ctypes.c_long
         L.cref_last_error.restype = ctypes.c_char_p
         L.cref_net_create.restype = vp
@@ -367,13 +380,16 @@ def ref_lib():
         L.cref_net_calculate_error.argtypes = [vp, c_float_p]
         L.cref_net_count_correct.argtypes = [vp, c_int_p]
         L.cref_lstm_get_internal.argtypes = [vp, ci, ci, c_float_p, cl]
-        _ref = L
-    return _ref
+        if omp:
+            _ref_omp = L
+        else:
+            _ref = L
+    return _ref_omp if omp else _ref
 
 
 class RefNet:
-    def __init__(self, net_json, S, maxT):
-        self.L = ref_lib()
+    def __init__(self, net_json, S, maxT, omp=False):
+        self.L = ref_lib(omp)
         if not isinstance(net_json, str):
             net_json = json.dumps(net_json)
         self.h = self.L.cref_net_create(net_json.encode(), S, maxT)
