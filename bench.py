@@ -164,9 +164,13 @@ def cpu_reference_best(steps, warmup):
     cands = sorted({n for n in (ncpu, ncpu // 2, 64, 32, 16, 8) if 1 < n <= ncpu})
     if not cands:
         return single, single
-    probe = {n: cpu_reference_rate(1, 1, threads=n)["value"] for n in cands}
-    best_n = max(probe, key=probe.get)
-    best = cpu_reference_rate(steps, warmup, threads=best_n)
+    try:
+        probe = {n: cpu_reference_rate(1, 1, threads=n)["value"] for n in cands}
+        best_n = max(probe, key=probe.get)
+        best = cpu_reference_rate(steps, warmup, threads=best_n)
+    except OSError as e:                               # no OpenMP runtime on this host: the single-threaded build is the baseline
+        print("bench: OpenMP reference build unusable (%s)" % e, file=sys.stderr)
+        return single, single
     return (best if best["value"] > single["value"] else single), single
 
 
