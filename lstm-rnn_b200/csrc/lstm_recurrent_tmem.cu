@@ -1,6 +1,6 @@
-// Persistent recurrent FORWARD kernel, tensor-memory-resident variant ("v4"): same decomposition, exchange buffer and step-counter
+// Persistent recurrent kernels, tensor-memory-resident variant ("v4"): same decomposition, L2 exchange buffers and step-counter
 // protocol as lstm_recurrent_reg.cu, but the CTA's slice of the recurrent weights lives in TENSOR MEMORY for the whole pass and the
-// per-timestep product runs on the tensor cores (tcgen05.mma with the A operand in TMEM):
+// per-timestep product runs on the tensor cores (tcgen05.mma with the A operand in TMEM).  Forward:
 //
 //     pre[128 rows x NB seqs] = Wslice[128 x Hp] * hprev[Hp x NB]          row = gate*32 + cell, NB = 16 or 32
 //
@@ -12,9 +12,11 @@
 // reference's own serial fp32 sum is at 4.4e-7 -- and 1.57 k cycles for the 80 MMAs of a C2 step against 4.8 k for the FFMA GEMM.)
 //
 // Per step the B operand -- the previous-step vector of the CTA's sequences -- is split while it is copied from the L2 exchange buffer
-// into three K-major SWIZZLE_128B shared tiles (tf32 hi, tf32 lo, bf16), one elected thread issues the MMAs, and warps 0..3 (gate =
-// warp, cell = lane) pull the accumulator out of TMEM and stage it [gate][seq][cell] for the gate math, which is unchanged.
-// Used when pad32(H) <= 256 and BLSTM_REC_V=3 selects it; lstm_recurrent_reg.cu / lstm_recurrent.cu remain the other families.
+// into K-major SWIZZLE_128B shared tiles (tf32 hi and lo as the two halves of one tile, bf16), one elected thread issues the MMAs,
+// and warps 0..3 (gate = warp, cell = lane) pull the accumulator out of TMEM and stage it [gate][seq][cell] for the gate math, which
+// is unchanged.  The BPTT kernel (second half of this file) slices the product the other way round so that its B operand never
+// crosses the exchange buffer.  Both are the default whenever pad32(H) <= 256 (bl_lstm_plan_create; BLSTM_REC_V=1 / 2 select the
+// register- / shared-memory-resident families of lstm_recurrent_reg.cu / lstm_recurrent.cu instead).
 #include "lstm_recurrent.cuh"
 #include <cuda_bf16.h>
 #include <cmath>
