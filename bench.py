@@ -344,7 +344,17 @@ def run_ours(args, rank, world, local_rank):
                     "algorithmic_bytes_per_launch": (fwd_b + bwd_b) / max(n_launch, 1), "avg_launch_ms": rec_ms / max(n_launch, 1),
                     "share_of_kernel_time": share[1] + share[2]}
         h2d = sum(f.N * (123 * 4 + 4) for f in timed) / K + sum(f.N for f in timed) / K * len(layer_shapes(net_json))
-        base, single = cpu_reference_best(4, 1) if world == 1 else (None, None)
+        base = single = None
+        if world == 1:
+            # in its own process: an OpenMP runtime that shares a process with torch's runs the reference build several times slower
+            try:
+                sub = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--steps", "4", "--warmup", "1"],
+                                     capture_output=True, text=True, timeout=900)
+                ref = json.loads(sub.stdout.strip().splitlines()[-1])
+                base, single = ref["cpu_baseline"], ref["single_thread"]
+            except Exception as e:
+                print("bench: reference subprocess failed (%s); timing it in-process" % e, file=sys.stderr)
+                base, single = cpu_reference_best(4, 1)
         line = {"metric": METRIC, "value": total_frames / (dev_ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
                 "ms_per_step": e2e_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
                 "data": "synthetic",
