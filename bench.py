@@ -10,7 +10,8 @@ forward -> error -> backward -> per-layer gradient all-reduce (N>1) -> SGD+momen
   e2e   : valid frames/s through the host C ABI with HOST (pinned) buffers: H2D of the fraction and D2H of the objective
           inside the timed region; K steps bracketed by barrier + synchronize, max over ranks
   roofline / kernel_classes : per-kernel-class device time measured live with CUDA events on the launch stream
-  cpu_baseline : the reference's CPU path (oracle/_ref, built from /root/reference) on 1 host core, bounded sample
+  cpu_baseline : the reference's CPU path (oracle/_ref, built from /root/reference) on a bounded sample: its OpenMP-host-backend
+          build on all host threads, with the rate of its own single-threaded build configuration beside it
 Synthetic data: frames N(0,1), weights U(-0.1,0.1), lengths clip(lognormal(ln 290, .35), 90, 780), lr 1e-4, momentum .9.
 """
 import argparse
@@ -35,7 +36,15 @@ METRIC, UNIT = "train_frames_per_sec", "frames/s"
 WORKLOAD = {
     "C2": "C2 TIMIT-shape deep BLSTM: input 123 -> 3 x blstm 500 (250 cells/direction) -> softmax 183 -> multiclass CE, "
           "parallel_sequences=100 per GPU, synthetic frames, lengths clip(lognormal(ln290,.35),90,780)",
+    # the other BASELINE.json configs are parity-test cases (tests/test_gpu_parity.py); --workload measures them on request
+    "C3": "C3 CHiME recognition BLSTM: input 39 -> blstm 156 -> blstm 300 -> blstm 102 -> softmax 51 -> multiclass CE, "
+          "parallel_sequences=50 per GPU, synthetic frames, lengths U[113,152]",
+    "C4": "C4 CHiME autoencoding BLSTM: input 39 -> blstm 156 -> blstm 256 -> blstm 156 -> feedforward_identity 39 -> sse, "
+          "truncate_seq=64, parallel_sequences=50 per GPU, synthetic noisy/clean pairs, lengths U[113,152]",
+    "C5": "C5 LVCSR-shape BLSTM: input 123 -> 5 x blstm 1024 (512 cells/direction) -> softmax 8000 -> multiclass CE, truncate_seq=500, "
+          "parallel_sequences=16 per GPU (128 on 8 GPUs), synthetic frames, lengths clip(lognormal(ln800,.4),200,2000)",
 }
+WORKLOAD_SEED = {"C2": 2, "C3": 3, "C4": 4, "C5": 5}
 
 
 def peaks():
@@ -84,6 +93,21 @@ def c2_sequences(num_seqs, seed=2):
     lengths = synth.sequence_lengths(cfg, num_seqs, seed)
     xs, cs, _ = synth.make_sequences(lengths, 123, seed, classes=183)
     return cfg, lengths, xs, cs
+
+
+def workload_sequences(name, num_seqs):
+    """Synthetic sequences of a BASELINE.json config: (cfg, lengths, inputs, class targets | None, dense targets | None,
+    input size, output size).  For C2 this is exactly c2_sequences()."""
+    cfg = synth.config(name)
+    seed = WORKLOAD_SEED[name]
+    layers = json.loads(cfg["net"])["layers"]
+    P, O = layers[0]["size"], layers[-1]["size"]
+    lengths = synth.sequence_lengths(cfg, num_seqs, seed)
+    if cfg["classes"]:
+        xs, cs, ts = synth.make_sequences(lengths, P, seed, classes=cfg["classes"])
+    else:
+        xs, cs, ts = synth.make_sequences(lengths, P, seed, target_size=O)
+    return cfg, lengths, xs, cs, ts, P, O
 
 
 def layer_shapes(net_json):
@@ -205,11 +229,13 @@ def run_ours(args, rank, world, local_rank):
     k, h = cb.libs()
 
     K, W = args.steps, args.warmup
-    cfg, lengths, xs, cs = c2_sequences((K + W) * 100 * world)
-    S = cfg["S"]
+    wl = args.workload
+    S = 16 if wl == "C5" else synth.config(wl)["S"]              # per GPU (weak scaling); C5's 128 is the 8-GPU global figure
+    cfg, lengths, xs, cs, ts, P_in, O_out = workload_sequences(wl, (K + W) * S * world)
+    classification = cs is not None
     net_json = cfg["net"]
-    ds = cb.DataSet(ctx, xs, S, seq_classes=cs, O=183, truncate=cfg["truncate"], training=True, rank=rank, world=world)
-    del xs, cs
+    ds = cb.DataSet(ctx, xs, S, seq_classes=cs, seq_targets=ts, O=O_out, truncate=cfg["truncate"], training=True, rank=rank, world=world)
+    del xs, cs, ts
     net = cb.Net(ctx, net_json, S, ds.max_len)
     for i, w in enumerate(synth.init_weights(net_json, 3)):
         if len(w):
@@ -267,7 +293,8 @@ def run_ours(args, rank, world, local_rank):
             e0.record(stream)
             net.forward()
             net.calculate_error()
-            net.count_correct()
+            if classification:
+                net.count_correct()
             net.backward()
             opt.update_weights()
             e1.record(stream)
@@ -343,9 +370,10 @@ def run_ours(args, rank, world, local_rank):
                     "frac": achieved / pk["hbm_gbs"], "peak_source": pk["source"], "traffic": traffic,
                     "algorithmic_bytes_per_launch": (fwd_b + bwd_b) / max(n_launch, 1), "avg_launch_ms": rec_ms / max(n_launch, 1),
                     "share_of_kernel_time": share[1] + share[2]}
-        h2d = sum(f.N * (123 * 4 + 4) for f in timed) / K + sum(f.N for f in timed) / K * len(layer_shapes(net_json))
+        # inputs + targets (int class or dense row) + one patTypes byte per slot and layer
+        h2d = sum(f.N * (P_in * 4 + (4 if classification else O_out * 4)) for f in timed) / K + sum(f.N for f in timed) / K * len(layer_shapes(net_json))
         base = single = None
-        if world == 1:
+        if world == 1 and wl == "C2":
             # in its own process: an OpenMP runtime that shares a process with torch's runs the reference build several times slower
             try:
                 sub = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--steps", "4", "--warmup", "1"],
@@ -358,9 +386,10 @@ def run_ours(args, rank, world, local_rank):
         line = {"metric": METRIC, "value": total_frames / (dev_ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
                 "ms_per_step": e2e_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
                 "data": "synthetic",
-                "config": {"workload": WORKLOAD["C2"], "parallel_sequences_per_gpu": S, "gemm_mode": args.mode,
+                "config": {"workload": WORKLOAD[wl], "parallel_sequences_per_gpu": S, "gemm_mode": args.mode,
                            "frames_per_step": total_frames / K, "slots_per_step_per_gpu": slots / K,
-                           "l2": "inputs larger than L2: every step touches ~%.1f GB of activations/deltas per GPU" % (slots / K * 2000 * 4 * 2 * 3 / 1e9),
+                           "l2": "inputs larger than L2: every step touches ~%.1f GB of activations/deltas per GPU"
+                                 % (slots / K * sum(4 * L for t, L, _ in layer_shapes(net_json) if t in ("lstm", "blstm")) * 4 * 2 / 1e9),
                            "plan": plan},
                 "e2e": {"value": total_frames / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 8},
                 "device_ms_per_step": dev_ms / K, "gpu_launches": launches, "clocks": clocks, "roofline": roofline,
@@ -384,11 +413,15 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--mode", default="strict", choices=["strict", "fast"])
+    ap.add_argument("--workload", default="C2", choices=sorted(WORKLOAD),
+                    help="BASELINE.json config to measure; the default C2 is the one the metric is quoted on (the reference arm and cpu_baseline are C2 only)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
     local_rank = int(os.environ.get("LOCAL_RANK", 0))
     if args.impl == "reference":
+        if args.workload != "C2":
+            raise SystemExit("bench.py --impl reference times the C2 workload only")
         run_reference(args, rank)
         return
     if args.warmup < 3:
