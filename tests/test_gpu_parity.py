@@ -457,6 +457,27 @@ def test_c2_network_against_oracle_short_sequences(oracle, gpu_ctx, family, monk
     print("C2 full-width (%s) worst rel err %.2e" % (family, worst))
 
 
+LONG_CASES = [
+    # name, net, S, lengths: production-width recurrences over hundreds of timesteps -- the rounding of the tensor-core step GEMM
+    # compounds through c and h, so short-sequence parity does not cover it (LstmLayer.cu:763-886, 888-1051)
+    ("h250_T300", synth.network_json(41, [500], 33), 16, [212, 230, 241, 250, 250, 263, 270, 271, 280, 284, 290, 293, 297, 299, 300, 300]),
+    ("h512_T100", synth.network_json(41, [1024], 33), 8, [61, 77, 85, 90, 96, 99, 100, 100]),
+    ("h12_ragged_T780", synth.network_json(7, [("lstm", 12), 10], 5), 4, [90, 300, 779, 780]),
+    ("h125_two_layers_T200", synth.network_json(23, [250, 250], 19), 10, [120, 133, 150, 158, 170, 177, 180, 190, 199, 200]),
+]
+
+
+@pytest.mark.parametrize("case", LONG_CASES, ids=[c[0] for c in LONG_CASES])
+def test_long_sequences_at_production_width(oracle, gpu_ctx, case):
+    """Every tensor of a long fraction against the oracle at the strict bar (~10-20 s of CPU oracle per case)."""
+    import currennt_b200 as cb
+    name, net_json, S, lengths = case
+    layers = json.loads(net_json)["layers"]
+    info = cb.Net(gpu_ctx, net_json, S, max(lengths) + 2).plan_info(1)
+    worst = check_net(oracle, gpu_ctx, net_json, S, lengths, layers[-1]["size"], 0, seed=17)
+    print(name, info, "worst rel err %.2e" % worst)
+
+
 def test_c3_chime_recognition_shape_against_oracle(oracle, gpu_ctx):
     """BASELINE config 3: the CHiME recognition recipe's network (39 -> blstm 156 -> blstm 300 -> blstm 102 -> softmax 51,
     S=50, examples/speech_recognition_chime/no_subsampling/network.jsn) at full width on sequences short enough for the oracle."""
