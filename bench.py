@@ -365,7 +365,7 @@ def run_ours(args, rank, world, local_rank):
             tj = json.load(open(tpath))
             traffic = (fwd_b / 40.0 * tj["fwd_dram_bytes_per_slot_per_layer_unit"] + bwd_b / 48.0 * tj["bwd_dram_bytes_per_slot_per_layer_unit"]) / max(n_launch, 1)
         plan = net.plan_info(2)
-        kfam = {"tmem": "tmem", "registers": "reg", "smem": "persistent"}
+        kfam = {"tm2": "tm2", "tmem": "tmem", "registers": "reg", "smem": "persistent"}
         roofline = {"kernel": "lstm_fwd_%s_kernel + lstm_bwd_%s_kernel" % (kfam[plan["fwd_kernel"]], kfam[plan["bwd_kernel"]]), "bound": "hbm", "achieved": achieved, "peak": pk["hbm_gbs"], "unit": "GB/s",
                     "frac": achieved / pk["hbm_gbs"], "peak_source": pk["source"], "traffic": traffic,
                     "algorithmic_bytes_per_launch": (fwd_b + bwd_b) / max(n_launch, 1), "avg_launch_ms": rec_ms / max(n_launch, 1),

@@ -40,6 +40,7 @@ int     cn_layer_get_output_errors(cn_net *net, int layer, float *host_dst, long
 int     cn_lstm_get_internal(cn_net *net, int layer, int dir, int which, float *host_dst, long n);
 int     cn_lstm_plan_info(cn_net *net, int layer, int *out8);
 int     cn_lstm_debug_trace(cn_net *net, int layer, int T, long long *host_dst, int *rows);
+int     cn_lstm_debug_trace2(cn_net *net, int layer, int backward, int T, long long *host_dst, int *rows);   /* tm2 kernels: 8 stamps per step */
 /* serialises {"layers":..., "weights":...} (NeuralNetwork.cpp:192-235); returns the length needed (incl. NUL) */
 long    cn_net_export_json(cn_net *net, char *buf, long cap);
 

@@ -28,8 +28,10 @@ struct bl_lstm_plan {
     bl::RecGeom gf, gb;
     bool reg_f, reg_b;       // register-resident persistent kernels (lstm_recurrent_reg.cu) vs shared-memory ones
     bool tm_f, tm_b;         // tensor-memory-resident weights + tcgen05 step GEMM (lstm_recurrent_tmem.cu)
+    bool t2_f, t2_b;         // second tensor-memory generation: in-band exchange, fp16 operands (lstm_recurrent_tm2.cu)
     float *acts, *deltas, *cst, *cerr, *hx, *dx, *gpart;
-    long long *trace;
+    long long *trace, *trace_b;
+    bool no_fused_split;     // BLSTM_NO_FUSED_SPLIT, read once at plan creation
     float *tcbuf;            // prepared tensor-core operands (hi then lo of each): X, Win (forward); deltas, Y, Win re-blocked (backward)
     size_t tcbuf_elems;
     float *tc_X, *tc_Wf, *tc_D, *tc_Y, *tc_Wb;
@@ -122,7 +124,8 @@ int bl_lstm_plan_create(bl_ctx *ctx, int P, int L, int bidirectional, int S, int
     pl->S = S; pl->maxT = maxT; pl->bias = bias; pl->lastT = 0;
     pl->acts = pl->deltas = pl->cst = pl->cerr = pl->hx = pl->dx = pl->gpart = nullptr;
     pl->flags_f = pl->flags_b = nullptr;
-    pl->trace = nullptr;
+    pl->trace = pl->trace_b = nullptr;
+    pl->no_fused_split = getenv("BLSTM_NO_FUSED_SPLIT") != nullptr;
     pl->tcbuf = nullptr; pl->tcbuf_elems = 0;
     pl->xsplit_src = nullptr; pl->xsplit_ld = 0; pl->xsplit_T = 0; pl->ysplit_T = 0;
 
@@ -132,20 +135,26 @@ int bl_lstm_plan_create(bl_ctx *ctx, int P, int L, int bidirectional, int S, int
     // weights, else shared memory; BLSTM_REC_V=1 skips the tensor-memory kernels, BLSTM_REC_V=2 forces the shared-memory ones)
     const char *ef = getenv("BLSTM_FWD_G"), *eb = getenv("BLSTM_BWD_G"), *nf = getenv("BLSTM_FWD_NSUB"), *nb = getenv("BLSTM_BWD_NSUB"),
                *tf = getenv("BLSTM_FWD_NT"), *tb = getenv("BLSTM_BWD_NT"), *ev = getenv("BLSTM_REC_V");
+    // kernel family: 0 (default) = best that fits: tm2, else tensor-memory generation 1, else register-resident, else shared memory;
+    // 1 = register-resident first, 2 = shared memory only, 3 = tensor-memory generation 1 first, 4 = tm2 first (same as 0)
     const int family = ev ? atoi(ev) : 0;
-    const bool want_reg = family != 2, want_tmem = family == 0 || family == 3;
-    pl->tm_f = want_tmem && bl::choose_geometry_tmem(pl->H, S, pl->ndir, ctx->num_sms, cap, ef ? atoi(ef) : 0, &pl->gf);
-    pl->reg_f = !pl->tm_f && want_reg && bl::choose_geometry_reg(false, pl->H, S, pl->ndir, ctx->num_sms, cap, ef ? atoi(ef) : 0, &pl->gf);
-    pl->tm_b = want_tmem && bl::choose_geometry_tmem_bwd(pl->H, S, pl->ndir, ctx->num_sms, cap, eb ? atoi(eb) : 0, &pl->gb);
-    pl->reg_b = !pl->tm_b && want_reg && bl::choose_geometry_reg(true, pl->H, S, pl->ndir, ctx->num_sms, cap, eb ? atoi(eb) : 0, &pl->gb);
-    if ((!pl->tm_f && !pl->reg_f && !bl::choose_geometry(false, pl->H, S, pl->ndir, ctx->num_sms, cap, ef ? atoi(ef) : 0, nf ? atoi(nf) : 0, tf ? atoi(tf) : 0, &pl->gf)) ||
-        (!pl->tm_b && !pl->reg_b && !bl::choose_geometry(true, pl->H, S, pl->ndir, ctx->num_sms, cap, eb ? atoi(eb) : 0, nb ? atoi(nb) : 0, tb ? atoi(tb) : 0, &pl->gb))) {
+    const bool want_reg = family != 2, want_tmem = family == 0 || family == 3 || family == 4, want_t2 = family == 0 || family == 4;
+    const int fG = ef ? atoi(ef) : 0, bG = eb ? atoi(eb) : 0;
+    pl->t2_f = want_t2 && bl::choose_geometry_tm2(false, pl->H, S, pl->ndir, ctx->num_sms, ctx->smem_optin - 1024, fG, &pl->gf);
+    pl->tm_f = !pl->t2_f && want_tmem && bl::choose_geometry_tmem(pl->H, S, pl->ndir, ctx->num_sms, cap, fG, &pl->gf);
+    pl->reg_f = !pl->t2_f && !pl->tm_f && want_reg && bl::choose_geometry_reg(false, pl->H, S, pl->ndir, ctx->num_sms, cap, fG, &pl->gf);
+    pl->t2_b = want_t2 && bl::choose_geometry_tm2(true, pl->H, S, pl->ndir, ctx->num_sms, ctx->smem_optin - 1024, bG, &pl->gb);
+    pl->tm_b = !pl->t2_b && want_tmem && bl::choose_geometry_tmem_bwd(pl->H, S, pl->ndir, ctx->num_sms, cap, bG, &pl->gb);
+    pl->reg_b = !pl->t2_b && !pl->tm_b && want_reg && bl::choose_geometry_reg(true, pl->H, S, pl->ndir, ctx->num_sms, cap, bG, &pl->gb);
+    if ((!pl->t2_f && !pl->tm_f && !pl->reg_f && !bl::choose_geometry(false, pl->H, S, pl->ndir, ctx->num_sms, cap, fG, nf ? atoi(nf) : 0, tf ? atoi(tf) : 0, &pl->gf)) ||
+        (!pl->t2_b && !pl->tm_b && !pl->reg_b && !bl::choose_geometry(true, pl->H, S, pl->ndir, ctx->num_sms, cap, bG, nb ? atoi(nb) : 0, tb ? atoi(tb) : 0, &pl->gb))) {
         delete pl;
         return bl::fail(ctx, "bl_lstm_plan_create: no persistent-kernel geometry fits (H=%d S=%d): recurrent weights do not fit on chip",
                         L / (bidirectional ? 2 : 1), S);
     }
     const size_t N = (size_t)maxT * S;
-    const size_t hx_elems = (size_t)pl->ndir * 2 * S * pl->gf.RS, dx_elems = (size_t)pl->ndir * 2 * S * pl->gb.RS;
+    const size_t hx_elems = pl->t2_f ? pl->gf.xelems : (size_t)pl->ndir * 2 * S * pl->gf.RS;
+    const size_t dx_elems = pl->t2_b ? pl->gb.xelems : (size_t)pl->ndir * 2 * S * pl->gb.RS;
     pl->gsplit = 64;
     int rc = 0;
     rc |= bl_malloc(ctx, (void **)&pl->acts, N * 4 * L * sizeof(float));
@@ -157,8 +166,10 @@ int bl_lstm_plan_create(bl_ctx *ctx, int P, int L, int bidirectional, int S, int
     rc |= bl_malloc(ctx, (void **)&pl->gpart, (size_t)pl->gsplit * 7 * L * sizeof(float));
     rc |= bl_malloc(ctx, (void **)&pl->flags_f, (size_t)pl->ndir * pl->gf.G * 32 * sizeof(unsigned));
     rc |= bl_malloc(ctx, (void **)&pl->flags_b, (size_t)pl->ndir * pl->gb.G * 32 * sizeof(unsigned));
-    if (getenv("BLSTM_REC_TRACE"))
-        rc |= bl_malloc(ctx, (void **)&pl->trace, (size_t)ctx->num_sms * 4 * maxT * 6 * sizeof(long long));
+    if (getenv("BLSTM_REC_TRACE")) {
+        rc |= bl_malloc(ctx, (void **)&pl->trace, (size_t)ctx->num_sms * 4 * maxT * 8 * sizeof(long long));
+        rc |= bl_malloc(ctx, (void **)&pl->trace_b, (size_t)ctx->num_sms * maxT * 8 * sizeof(long long));
+    }
     if (rc) { bl_lstm_plan_destroy(pl); return 1; }
     // zero-filled like the reference's buffers (LstmLayer.cu:554); the exchange buffers' padding columns must stay zero
     rc |= bl_memset(ctx, pl->acts, 0, N * 4 * L * sizeof(float));
@@ -176,7 +187,7 @@ void bl_lstm_plan_destroy(bl_lstm_plan *pl)
 {
     if (!pl) return;
     cudaStreamSynchronize(pl->ctx->stream);
-    void *bufs[] = { pl->acts, pl->deltas, pl->cst, pl->cerr, pl->hx, pl->dx, pl->gpart, pl->flags_f, pl->flags_b, pl->trace, pl->tcbuf };
+    void *bufs[] = { pl->acts, pl->deltas, pl->cst, pl->cerr, pl->hx, pl->dx, pl->gpart, pl->flags_f, pl->flags_b, pl->trace, pl->trace_b, pl->tcbuf };
     for (void *b : bufs) if (b) cudaFree(b);
     delete pl;
 }
@@ -184,11 +195,11 @@ void bl_lstm_plan_destroy(bl_lstm_plan *pl)
 int bl_lstm_plan_info(const bl_lstm_plan *pl, int *o)
 {
     // smem is a multiple of 4: the low two bits carry nsub (1, 2, 4 -> 1, 2, 0), or 3 for the register-resident kernels
-    // (the tensor-memory forward kernel reports its smem rounded up to 16 with 11 in the low four bits)
+    // (the tensor-memory kernels report their smem rounded up to 16 with 11 (generation 1) or 13 (tm2) in the low four bits)
     o[0] = pl->gf.G; o[1] = pl->gf.C; o[2] = pl->gf.CL;
-    o[3] = pl->tm_f ? (int)((pl->gf.smem + 15) & ~(size_t)15) + 11 : (int)pl->gf.smem + (pl->reg_f ? 3 : pl->gf.nsub);
+    o[3] = pl->t2_f ? (int)((pl->gf.smem + 15) & ~(size_t)15) + 13 : pl->tm_f ? (int)((pl->gf.smem + 15) & ~(size_t)15) + 11 : (int)pl->gf.smem + (pl->reg_f ? 3 : pl->gf.nsub);
     o[4] = pl->gb.G; o[5] = pl->gb.C; o[6] = pl->gb.CL;
-    o[7] = pl->tm_b ? (int)((pl->gb.smem + 15) & ~(size_t)15) + 11 : (int)pl->gb.smem + (pl->reg_b ? 3 : pl->gb.nsub);
+    o[7] = pl->t2_b ? (int)((pl->gb.smem + 15) & ~(size_t)15) + 13 : pl->tm_b ? (int)((pl->gb.smem + 15) & ~(size_t)15) + 11 : (int)pl->gb.smem + (pl->reg_b ? 3 : pl->gb.nsub);
     return 0;
 }
 
@@ -249,12 +260,12 @@ int bl_lstm_forward(bl_lstm_plan *pl, const float *W, const float *X, int ldx, c
     // the tensor-core backward pass wants the TF32 split of Y: the register-resident kernel writes it while it stores Y
     p.ys_hi = p.ys_lo = nullptr; p.ld_ys = 0;
     pl->ysplit_T = 0;
-    if ((pl->reg_f || pl->tm_f) && bl::tc_wanted(ctx, P, 4 * L, N) && getenv("BLSTM_NO_FUSED_SPLIT") == nullptr) {
+    if ((pl->reg_f || pl->tm_f || pl->t2_f) && bl::tc_wanted(ctx, P, 4 * L, N) && !pl->no_fused_split) {
         BL_CHECK(plan_tc_buffers(pl));
         p.ys_hi = pl->tc_Y; p.ys_lo = pl->tc_Y + pl->tc_eY; p.ld_ys = (int)bl::tc_operand_ld(pl->ndir * ((H + 3) & ~3));
         pl->ysplit_T = T;
     }
-    BL_CHECK(pl->tm_f ? bl::launch_lstm_fwd_tmem(ctx, p) : pl->reg_f ? bl::launch_lstm_fwd_reg(ctx, p) : bl::launch_lstm_fwd(ctx, p));
+    BL_CHECK(pl->t2_f ? bl::launch_lstm_fwd_tm2(ctx, p) : pl->tm_f ? bl::launch_lstm_fwd_tmem(ctx, p) : pl->reg_f ? bl::launch_lstm_fwd_reg(ctx, p) : bl::launch_lstm_fwd(ctx, p));
     pl->lastT = T;
     return 0;
 }
@@ -278,13 +289,13 @@ int bl_lstm_backward(bl_lstm_plan *pl, const float *W, const float *X, int ldx, 
     p.dx = pl->dx; p.flags = pl->flags_b; p.pat = patTypes;
     p.T = T; p.Tmin = Tmin; p.S = S; p.H = H; p.L = L; p.ndir = pl->ndir; p.g = pl->gb;
     const bool tc = bl::tc_wanted(ctx, P, 4 * L, N);
-    const bool fused_dsplit = tc && (pl->reg_b || pl->tm_b) && getenv("BLSTM_NO_FUSED_SPLIT") == nullptr;
-    p.ds_hi = p.ds_lo = nullptr; p.ld_ds = 0;
+    const bool fused_dsplit = tc && (pl->reg_b || pl->tm_b || pl->t2_b) && !pl->no_fused_split;
+    p.ds_hi = p.ds_lo = nullptr; p.ld_ds = 0; p.trace = pl->trace_b;
     if (fused_dsplit) {
         BL_CHECK(plan_tc_buffers(pl));
         p.ds_hi = pl->tc_D; p.ds_lo = pl->tc_D + pl->tc_eD; p.ld_ds = (int)bl::tc_operand_ld(4 * pl->ndir * ((H + 3) & ~3));
     }
-    BL_CHECK(pl->tm_b ? bl::launch_lstm_bwd_tmem(ctx, p) : pl->reg_b ? bl::launch_lstm_bwd_reg(ctx, p) : bl::launch_lstm_bwd(ctx, p));
+    BL_CHECK(pl->t2_b ? bl::launch_lstm_bwd_tm2(ctx, p) : pl->tm_b ? bl::launch_lstm_bwd_tmem(ctx, p) : pl->reg_b ? bl::launch_lstm_bwd_reg(ctx, p) : bl::launch_lstm_bwd(ctx, p));
 
     if (tc) {
         // ---- tensor-core path: every operand is split (hi/lo TF32) ONCE per layer, in its own row-major layout, and read
@@ -371,9 +382,23 @@ int bl_lstm_backward(bl_lstm_plan *pl, const float *W, const float *X, int ldx, 
 int bl_lstm_debug_trace(bl_lstm_plan *pl, int T, long long *host_dst, int *rows)
 {
     if (!pl->trace) return bl::fail(pl->ctx, "tracing is off (set BLSTM_REC_TRACE before creating the plan)");
+    if (pl->t2_f) return bl::fail(pl->ctx, "the tm2 kernels record 8 stamps per step: use bl_lstm_debug_trace2");
     const int n = pl->ndir * (pl->gf.G / pl->gf.nsub) * pl->gf.C * pl->gf.nsub;
     *rows = n;
     BL_CUDA(pl->ctx, cudaMemcpyAsync(host_dst, pl->trace, (size_t)n * T * 6 * sizeof(long long), cudaMemcpyDeviceToHost, pl->ctx->stream));
+    BL_CUDA(pl->ctx, cudaStreamSynchronize(pl->ctx->stream));
+    return 0;
+}
+
+int bl_lstm_debug_trace2(bl_lstm_plan *pl, int backward, int T, long long *host_dst, int *rows)
+{
+    const long long *src = backward ? pl->trace_b : pl->trace;
+    if (!src) return bl::fail(pl->ctx, "tracing is off (set BLSTM_REC_TRACE before creating the plan)");
+    if (backward ? !pl->t2_b : !pl->t2_f) return bl::fail(pl->ctx, "bl_lstm_debug_trace2: the plan does not run the tm2 kernel for this pass");
+    const bl::RecGeom &g = backward ? pl->gb : pl->gf;
+    const int n = pl->ndir * g.G * g.C;
+    *rows = n;
+    BL_CUDA(pl->ctx, cudaMemcpyAsync(host_dst, src, (size_t)n * T * 8 * sizeof(long long), cudaMemcpyDeviceToHost, pl->ctx->stream));
     BL_CUDA(pl->ctx, cudaStreamSynchronize(pl->ctx->stream));
     return 0;
 }

@@ -27,6 +27,7 @@ struct RecGeom {
     int Hpad;
     size_t smem;
     double cost;
+    size_t xelems;          // tm2 kernels: floats of the exchange buffer (0 = the plan's default ndir*2*S*RS)
 };
 
 bool choose_geometry(bool bwd, int H, int S, int ndir, int num_sms, int smem_cap, int forceG, int forceNsub, int forceNT, RecGeom *out);
@@ -60,6 +61,7 @@ struct RecBwdParams {
     int T, Tmin, S, H, L, ndir;
     // optional (register-resident kernels only): TF32 split of the deltas, hi/lo [N][ld_ds], column (gate*ndir + d)*Hq + j
     float *ds_hi, *ds_lo; int ld_ds;
+    long long *trace;               // optional [CTAs][T][8] clock64 stamps (tm2 kernels, BLSTM_REC_TRACE), else NULL
     RecGeom g;
 };
 
@@ -73,6 +75,12 @@ bool choose_geometry_tmem(int H, int S, int ndir, int num_sms, int smem_cap, int
 int launch_lstm_fwd_tmem(bl_ctx *ctx, const RecFwdParams &p);
 bool choose_geometry_tmem_bwd(int H, int S, int ndir, int num_sms, int smem_cap, int forceG, RecGeom *out);
 int launch_lstm_bwd_tmem(bl_ctx *ctx, const RecBwdParams &p);
+
+// second tensor-memory generation (lstm_recurrent_tm2.cu): in-band exchange, fp16 two-term operands, warp-specialised step;
+// forward up to Hp = 512 and BPTT up to R = 512 (W_lo' in shared memory where TMEM alone is too small)
+bool choose_geometry_tm2(bool bwd, int H, int S, int ndir, int num_sms, int smem_cap, int forceG, RecGeom *out);
+int launch_lstm_fwd_tm2(bl_ctx *ctx, const RecFwdParams &p);
+int launch_lstm_bwd_tm2(bl_ctx *ctx, const RecBwdParams &p);
 
 int launch_lstm_fwd(bl_ctx *ctx, const RecFwdParams &p);
 int launch_lstm_bwd(bl_ctx *ctx, const RecBwdParams &p);

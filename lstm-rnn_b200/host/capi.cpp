@@ -127,6 +127,15 @@ int cn_lstm_debug_trace(cn_net *net, int i, int T, long long *dst, int *rows)
     return 0;
     CN_CATCH(1)
 }
+int cn_lstm_debug_trace2(cn_net *net, int i, int backward, int T, long long *dst, int *rows)
+{
+    CN_TRY
+    layers::LstmLayer *l = dynamic_cast<layers::LstmLayer *>(layerAt(net, i));
+    if (!l) throw std::runtime_error("not an lstm layer");
+    device::check(l->ctx(), bl_lstm_debug_trace2(l->plan(), backward, T, dst, rows));
+    return 0;
+    CN_CATCH(1)
+}
 long cn_net_export_json(cn_net *net, char *buf, long cap)
 {
     CN_TRY

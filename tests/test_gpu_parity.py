@@ -167,12 +167,14 @@ def test_network_forward_backward_parity(oracle, gpu_ctx, case):
     print(name, "worst rel err %.2e" % worst)
 
 
-@pytest.mark.parametrize("family", ["tmem", "registers"])
+FAMILY_ENV = {"tm2": "4", "tmem": "3", "registers": "1", "smem": "2"}
+
+
+@pytest.mark.parametrize("family", ["tm2", "tmem", "registers"])
 @pytest.mark.parametrize("G", [1, 2, 3])
 def test_sequence_group_geometries(oracle, gpu_ctx, G, family, monkeypatch):
     """The persistent kernels must give the same result for every (sequence groups x cell slices) decomposition."""
-    if family == "registers":
-        monkeypatch.setenv("BLSTM_REC_V", "1")
+    monkeypatch.setenv("BLSTM_REC_V", FAMILY_ENV[family])
     monkeypatch.setenv("BLSTM_FWD_G", str(G))
     monkeypatch.setenv("BLSTM_BWD_G", str(G))
     net_json = synth.network_json(11, [34, ("lstm", 21)], 9)
@@ -180,13 +182,13 @@ def test_sequence_group_geometries(oracle, gpu_ctx, G, family, monkeypatch):
     print("G=%d worst rel err %.2e" % (G, worst))
 
 
-@pytest.mark.parametrize("family", ["registers", "smem", "tmem"])
+@pytest.mark.parametrize("family", ["registers", "smem", "tmem", "tm2"])
 def test_both_recurrent_kernel_families(oracle, gpu_ctx, family, monkeypatch):
-    """Tensor-memory-resident (default where the slice fits: step GEMM on tcgen05 with the weights in TMEM), register-resident
-    (BLSTM_REC_V=1; the default for wider layers) and shared-memory-resident (BLSTM_REC_V=2, the fallback for slices that do not
-    fit the register file) kernels implement the same step protocol and must all hold the parity bar."""
+    """The four kernel families -- tm2 (default where the slice fits: in-band exchange, fp16 two-term step GEMM on tcgen05 with the
+    weights in TMEM), the first tensor-memory generation (BLSTM_REC_V=3: step counters, tf32 + bf16 operands), register-resident
+    (BLSTM_REC_V=1) and shared-memory-resident (BLSTM_REC_V=2, the last fallback) -- must all hold the parity bar."""
     import currennt_b200 as cb
-    monkeypatch.setenv("BLSTM_REC_V", {"registers": "1", "smem": "2", "tmem": "3"}[family])
+    monkeypatch.setenv("BLSTM_REC_V", FAMILY_ENV[family])
     net_json = synth.network_json(13, [48, ("lstm", 27)], 11)
     info = cb.Net(gpu_ctx, net_json, 6, 16).plan_info(1)
     assert info["fwd_kernel"] == family and info["bwd_kernel"] == family, info
@@ -202,32 +204,47 @@ TMEM_CASES = [
     ("cells_span_slices", synth.network_json(9, [("lstm", 70), 44], 6), 5, [1, 4, 7, 7, 9], 6, 2),
     ("h250_padded_k", synth.network_json(41, [500], 33), 12, [5, 7, 9, 9, 10, 12, 12, 12, 13, 13, 14, 14], 33, 0),
     ("h256_full_k", synth.network_json(17, [("lstm", 256)], 9), 7, [3, 4, 6, 6, 7, 9, 9], 9, 0),
+    ("h300_lo_in_smem_fwd", synth.network_json(9, [("lstm", 300)], 5), 6, [2, 5, 6, 8, 8, 9], 5, 0),
+    ("h450_blstm900", synth.network_json(11, [900], 7), 5, [3, 5, 6, 6, 7], 7, 0),
 ]
 
 
+@pytest.mark.parametrize("family", ["tmem", "tm2"])
 @pytest.mark.parametrize("case", TMEM_CASES, ids=[c[0] for c in TMEM_CASES])
-def test_tensor_memory_recurrent_kernels(oracle, gpu_ctx, case, monkeypatch):
-    """lstm_fwd_tmem_kernel / lstm_bwd_tmem_kernel (BLSTM_REC_V=3) against the oracle at the strict bar: N=16 and N=32 tiles, slices
-    with fewer than 32 cells, K padded from 250 to 256 and K = 256 exactly (two 128-row tiles in the BPTT kernel), one and several
-    sequence groups."""
+def test_tensor_memory_recurrent_kernels(oracle, gpu_ctx, case, family, monkeypatch):
+    """Both tensor-memory generations against the oracle at the strict bar: slices with fewer than 32 cells, K padded from 250 to 256
+    and K = 256 exactly (two 128-row tiles in the BPTT kernels), one and several sequence groups; generation 1 also with N=32 tiles
+    (more than 16 sequences per group -- tm2 leaves those geometries to it) and without its merged-N MMA."""
     import currennt_b200 as cb
     name, net_json, S, lengths, classes, G = case
+    if family == "tm2" and name == "one_group_n32":
+        pytest.skip("tm2 handles at most 16 sequences per group")
+    if family == "tmem" and name in ("h300_lo_in_smem_fwd", "h450_blstm900"):
+        pytest.skip("generation 1 holds at most 256 cells per direction")
+    monkeypatch.setenv("BLSTM_REC_V", FAMILY_ENV[family])
     if name.startswith("one_group"):           # also without the merged-N MMA (two tf32 products issued separately)
         monkeypatch.setenv("BLSTM_TM_MERGE", "0")
     if G:
         monkeypatch.setenv("BLSTM_FWD_G", str(G))
         monkeypatch.setenv("BLSTM_BWD_G", str(G))
     info = cb.Net(gpu_ctx, net_json, S, max(lengths) + 2).plan_info(1)
-    assert info["fwd_kernel"] == "tmem" and info["bwd_kernel"] == "tmem", info
+    assert info["fwd_kernel"] == family and info["bwd_kernel"] == family, info
     worst = check_net(oracle, gpu_ctx, net_json, S, lengths, classes, 0, seed=13)
     print(name, info, "worst rel err %.2e" % worst)
 
 
 def test_tensor_memory_kernel_falls_back_when_weights_do_not_fit(gpu_ctx, monkeypatch):
-    """pad32(H) > 256 does not fit the 512 TMEM columns: such layers keep the register / shared-memory kernels."""
+    """Generation 1: pad32(H) > 256 does not fit the 512 TMEM columns; tm2: more than 512 cells per direction fit neither TMEM nor
+    TMEM + shared memory.  Such layers keep the register / shared-memory kernels."""
     import currennt_b200 as cb
+    monkeypatch.setenv("BLSTM_REC_V", "3")
     info = cb.Net(gpu_ctx, synth.network_json(9, [("lstm", 300)], 4), 2, 6).plan_info(1)
-    assert info["fwd_kernel"] != "tmem" and info["bwd_kernel"] != "tmem", info
+    assert info["fwd_kernel"] not in ("tmem", "tm2") and info["bwd_kernel"] not in ("tmem", "tm2"), info
+    monkeypatch.delenv("BLSTM_REC_V")
+    info = cb.Net(gpu_ctx, synth.network_json(9, [("lstm", 600)], 4), 2, 6).plan_info(1)
+    assert info["fwd_kernel"] not in ("tmem", "tm2") and info["bwd_kernel"] not in ("tmem", "tm2"), info
+    info = cb.Net(gpu_ctx, synth.network_json(9, [("lstm", 512)], 4), 2, 6).plan_info(1)
+    assert info["fwd_kernel"] == "tm2" and info["bwd_kernel"] == "tm2", info
 
 
 def test_extreme_shapes(oracle, gpu_ctx):
@@ -443,13 +460,12 @@ def _full_net(gpu_ctx, name, S, maxT):
     return cfg, net, weights
 
 
-@pytest.mark.parametrize("family", ["tmem", "registers"])
+@pytest.mark.parametrize("family", ["tm2", "tmem", "registers"])
 def test_c2_network_against_oracle_short_sequences(oracle, gpu_ctx, family, monkeypatch):
     """The full TIMIT-shape network (123 -> 3 x blstm 500 -> softmax 183, S=100) against the oracle on a fraction short enough
     for the CPU oracle (T=10): every tensor within the strict bar.  Exercises the production geometry (G=9 x C=8 slices,
     register-resident weights) and the tcgen05 GEMMs at their real M/N."""
-    if family == "registers":                  # default: step GEMMs on tcgen05, weights in tensor memory (G=9 x C=8, N=16, K=256)
-        monkeypatch.setenv("BLSTM_REC_V", "1")
+    monkeypatch.setenv("BLSTM_REC_V", FAMILY_ENV[family])     # default: tm2 (step GEMMs on tcgen05, weights in tensor memory, G=9 x C=8)
     cfg = synth.config("C2")
     rng = np.random.default_rng(3)
     lengths = sorted(rng.integers(6, 11, 100).tolist())
@@ -467,11 +483,17 @@ LONG_CASES = [
 ]
 
 
+@pytest.mark.parametrize("family", ["default", "registers"])
 @pytest.mark.parametrize("case", LONG_CASES, ids=[c[0] for c in LONG_CASES])
-def test_long_sequences_at_production_width(oracle, gpu_ctx, case):
-    """Every tensor of a long fraction against the oracle at the strict bar (~10-20 s of CPU oracle per case)."""
+def test_long_sequences_at_production_width(oracle, gpu_ctx, case, family, monkeypatch):
+    """Every tensor of a long fraction against the oracle at the strict bar (~10-20 s of CPU oracle per case): the default kernels
+    (tm2, with W_lo' in shared memory at H = 512) and, at H = 512, the register-resident ones they replaced."""
     import currennt_b200 as cb
     name, net_json, S, lengths = case
+    if family == "registers":
+        if name != "h512_T100":
+            pytest.skip("register-resident kernels: the H = 512 case only")
+        monkeypatch.setenv("BLSTM_REC_V", "1")
     layers = json.loads(net_json)["layers"]
     info = cb.Net(gpu_ctx, net_json, S, max(lengths) + 2).plan_info(1)
     worst = check_net(oracle, gpu_ctx, net_json, S, lengths, layers[-1]["size"], 0, seed=17)

@@ -15,12 +15,14 @@
 #include <cmath>
 #include <vector>
 #include <cuda_runtime.h>
-#include <cuda_bf16.h>
+#include <cuda_fp16.h>
 
-constexpr int M = 128, N = 16, K = 256;
+constexpr int M = 128, N = 16, N2 = 32, K = 256;
 constexpr int NT = 256;
-constexpr int COL_AHI = 0, COL_ALO = 256, COL_D = 384, TMEM_COLS = 512;
-constexpr int BHI_BYTES = (K / 32) * 2048, BBF_BYTES = (K / 64) * 2048;
+constexpr int COL_AHI = 0, COL_ALO = 128, COL_D = 256, TMEM_COLS = 512;
+constexpr int KB_BYTES = N2 * 128;                  // one K-block (64 fp16 = 128 B per row) of the [h_hi | h_lo'] tile: 32 rows
+constexpr int B_BYTES = (K / 64) * KB_BYTES;
+constexpr float LO_SCALE = 2048.0f, LO_UNSCALE = 1.0f / 2048.0f;
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -34,14 +36,12 @@ __device__ __forceinline__ bool mbar_wait_bounded(uint64_t *bar, uint32_t parity
     }
     return false;
 }
-
 __device__ __forceinline__ bool elect_one()
 {
     uint32_t pred;
     asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
     return pred != 0;
 }
-
 // K-major, 128B-swizzled shared-memory matrix descriptor (same encoding as csrc/gemm_tc.cu): SBO = 1024 B, version 1, SWIZZLE_128B
 __device__ __forceinline__ uint64_t make_desc(const void *p)
 {
@@ -52,16 +52,10 @@ __device__ __forceinline__ uint64_t make_desc(const void *p)
     d |= (uint64_t)2 << 61;
     return d;
 }
-// D fp32; fmt: kind::tf32 -> 2 (tf32), kind::f16 -> 1 (bf16); both operands K-major
-__host__ __device__ constexpr uint32_t make_idesc(uint32_t fmt) { return (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24); }
+// D fp32, A and B fp16 (format 0 of kind::f16), both K-major, M = 128, N = n
+__host__ __device__ constexpr uint32_t make_idesc(int n) { return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(M >> 4) << 24); }
 
-__device__ __forceinline__ void mma_ts_tf32(uint32_t d, uint32_t a, uint64_t b, uint32_t idesc, uint32_t acc)
-{
-    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-                 "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
-                 :: "r"(d), "r"(a), "l"(b), "r"(idesc), "r"(acc) : "memory");
-}
-__device__ __forceinline__ void mma_ts_bf16(uint32_t d, uint32_t a, uint64_t b, uint32_t idesc, uint32_t acc)
+__device__ __forceinline__ void mma_ts_f16(uint32_t d, uint32_t a, uint64_t b, uint32_t idesc, uint32_t acc)
 {
     asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
                  "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
@@ -69,7 +63,6 @@ __device__ __forceinline__ void mma_ts_bf16(uint32_t d, uint32_t a, uint64_t b, 
 }
 __device__ __forceinline__ void commit(uint64_t *bar)
 { asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(smem_u32(bar)) : "memory"); }
-
 __device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&r)[8])
 {
     asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
@@ -87,34 +80,36 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16])
     for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
 
-__device__ __forceinline__ float tf32_rna(float x)
-{ uint32_t h; asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h) : "f"(x)); return __uint_as_float(h); }
-__device__ __forceinline__ uint32_t bf16_bits(float x) { return (uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(x)); }
+// x = hi + lo'/2^11 up to 2^-22 |x|
+__device__ __forceinline__ void split16(float x, uint32_t &hi, uint32_t &lo)
+{
+    const __half h = __float2half_rn(x);
+    hi = (uint32_t)__half_as_ushort(h);
+    lo = (uint32_t)__half_as_ushort(__float2half_rn(__fmul_rn(__fsub_rn(x, __half2float(h)), LO_SCALE)));
+}
 
-// byte offset of element (n, k) in a K-major SWIZZLE_128B tile of 16 rows: 128-byte rows, 8-row atoms of 1024 B, 16-byte chunks XORed
-// with the row index; one [16 x 128 B] box of 2048 B per K-block
-__device__ __forceinline__ int off_f32(int n, int k)
-{ const int kb = k >> 5, kin = k & 31, c = kin >> 2, e = kin & 3, r = n & 7; return kb * 2048 + (n >> 3) * 1024 + r * 128 + ((c ^ r) << 4) + e * 4; }
-__device__ __forceinline__ int off_bf16(int n, int k)
-{ const int kb = k >> 6, kin = k & 63, c = kin >> 3, e = kin & 7, r = n & 7; return kb * 2048 + (n >> 3) * 1024 + r * 128 + ((c ^ r) << 4) + e * 2; }
+// byte offset of element (row n, k) of the K-major SWIZZLE_128B tile of N2 rows: 128-byte rows (64 fp16), 8-row atoms of 1024 B,
+// 16-byte chunks XORed with the row index; one [N2 x 128 B] box per K-block
+__device__ __forceinline__ int off_f16(int n, int k)
+{ const int kb = k >> 6, kin = k & 63, c = kin >> 3, e = kin & 7, r = n & 7; return kb * KB_BYTES + (n >> 3) * 1024 + r * 128 + ((c ^ r) << 4) + e * 2; }
 
 struct Params {
     const float *W;        // [M][K]
-    const float *h;        // [N][K]   (the exchange buffer of the real kernel)
-    float *D;              // [M][N]   result of the last step (block 0)
-    long long *cyc;        // [4]      per-step cycles: total, write B, MMA issue..complete, tcgen05.ld
+    const float *h;        // [N][K]
+    float *D;              // [M][N]
+    long long *cyc;        // [4]
     int *err;
     int steps;
-    int terms;             // 1: hi*hi   2: + hi*lo   3: + bf16(lo)*bf16(hi)
-    int bf16_low_is_even;  // packing of two bf16 k values in one TMEM column
+    int terms;             // 1: hi*hi   2: + hi*lo'   3: + lo'*hi
+    int nrep;              // timing aid: repeat the MMA batch nrep times (same operands) to separate per-MMA cost from fixed cost
 };
 
 __global__ void __launch_bounds__(NT, 1) step_kernel(const Params p)
 {
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    uint8_t *Bhi = smem, *Blo = smem + BHI_BYTES, *Bbf = smem + 2 * BHI_BYTES;
-    uint64_t *bar = reinterpret_cast<uint64_t *>(smem + 2 * BHI_BYTES + BBF_BYTES);
+    uint8_t *B = smem;
+    uint64_t *bar = reinterpret_cast<uint64_t *>(smem + B_BYTES);
     uint32_t *slot = reinterpret_cast<uint32_t *>(bar + 1);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
@@ -131,48 +126,43 @@ __global__ void __launch_bounds__(NT, 1) step_kernel(const Params p)
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem = *slot;
 
-    // ---- weights into TMEM, once: lane = row m, column = k (tf32) / k pair (bf16)
+    // ---- weights into TMEM, once: lane = row m, column = k pair (even k in the low half)
     if (warp < 4) {
         const int m = warp * 32 + lane;
         const uint32_t lane_base = tmem + ((uint32_t)(warp * 32) << 16);
         const float *w = p.W + (size_t)m * K;
-        for (int c0 = 0; c0 < K; c0 += 8) {
-            uint32_t r[8];
-#pragma unroll
-            for (int i = 0; i < 8; ++i) r[i] = __float_as_uint(tf32_rna(w[c0 + i]));
-            tmem_st8(lane_base + COL_AHI + c0, r);
-        }
         for (int c0 = 0; c0 < K / 2; c0 += 8) {
-            uint32_t r[8];
+            uint32_t rh[8], rl[8];
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
-                const float x0 = w[2 * (c0 + i)], x1 = w[2 * (c0 + i) + 1];
-                const uint32_t b0 = bf16_bits(x0 - tf32_rna(x0)), b1 = bf16_bits(x1 - tf32_rna(x1));
-                r[i] = p.bf16_low_is_even ? (b0 | (b1 << 16)) : (b1 | (b0 << 16));
+                uint32_t h0, l0, h1, l1;
+                split16(w[2 * (c0 + i)], h0, l0); split16(w[2 * (c0 + i) + 1], h1, l1);
+                rh[i] = h0 | (h1 << 16); rl[i] = l0 | (l1 << 16);
             }
-            tmem_st8(lane_base + COL_ALO + c0, r);
+            tmem_st8(lane_base + COL_AHI + c0, rh);
+            tmem_st8(lane_base + COL_ALO + c0, rl);
         }
         asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
     }
+    for (int i = tid; i < B_BYTES / 4; i += NT) reinterpret_cast<uint32_t *>(B)[i] = 0u;
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 
-    const uint32_t idesc_tf32 = make_idesc(2), idesc_bf16 = make_idesc(1);
+    const uint32_t idesc32 = make_idesc(N2), idesc16 = make_idesc(N);
     long long c_total = 0, c_write = 0, c_mma = 0, c_ld = 0;
     float keep = 0.0f;
     bool ok = true;
     for (int s = 0; s < p.steps && ok; ++s) {
         const long long t0 = clock64();
-        // ---- B operand: the previous-step vector of the CTA's 16 sequences, split and written in the UMMA layout
+        // ---- B operand: previous-step vector of the CTA's sequences, split and written in the UMMA layout (rows n and N + n)
         for (int i = tid; i < N * K / 4; i += NT) {
             const int n = i / (K / 4), k = (i - n * (K / 4)) * 4;
             const float4 v = __ldcg(reinterpret_cast<const float4 *>(p.h + (size_t)n * K + k));
-            const float4 hi = make_float4(tf32_rna(v.x), tf32_rna(v.y), tf32_rna(v.z), tf32_rna(v.w));
-            *reinterpret_cast<float4 *>(Bhi + off_f32(n, k)) = hi;
-            *reinterpret_cast<float4 *>(Blo + off_f32(n, k)) = make_float4(v.x - hi.x, v.y - hi.y, v.z - hi.z, v.w - hi.w);
-            uint2 b; b.x = bf16_bits(v.x) | (bf16_bits(v.y) << 16); b.y = bf16_bits(v.z) | (bf16_bits(v.w) << 16);
-            *reinterpret_cast<uint2 *>(Bbf + off_bf16(n, k)) = b;
+            uint32_t h0, l0, h1, l1, h2, l2, h3, l3;
+            split16(v.x, h0, l0); split16(v.y, h1, l1); split16(v.z, h2, l2); split16(v.w, h3, l3);
+            *reinterpret_cast<uint2 *>(B + off_f16(n, k)) = make_uint2(h0 | (h1 << 16), h2 | (h3 << 16));
+            *reinterpret_cast<uint2 *>(B + off_f16(N + n, k)) = make_uint2(l0 | (l1 << 16), l2 | (l3 << 16));
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -181,20 +171,16 @@ __global__ void __launch_bounds__(NT, 1) step_kernel(const Params p)
         if (warp == 1) {
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             if (elect_one()) {
-                uint32_t acc = 0;
-                if (p.terms >= 3)
-                    for (int ks = 0; ks < K / 16; ++ks) {      // bf16: 16 k per MMA = 8 TMEM columns, 32 B in the swizzle atom
-                        mma_ts_bf16(tmem + COL_D, tmem + COL_ALO + ks * 8, make_desc(Bbf + (ks >> 2) * 2048) + (uint64_t)((ks & 3) * 2), idesc_bf16, acc);
-                        acc = 1;
+                for (int rep = 0; rep < p.nrep; ++rep) {
+                    // 16 k per MMA = 8 TMEM columns = 32 B inside the swizzle atom
+                    for (int ks = 0; ks < K / 16; ++ks) {
+                        const uint64_t bd = make_desc(B + (ks >> 2) * KB_BYTES) + (uint64_t)((ks & 3) * 2);
+                        if (p.terms >= 2) mma_ts_f16(tmem + COL_D, tmem + COL_AHI + ks * 8, bd, idesc32, (rep | ks) ? 1u : 0u);
+                        else              mma_ts_f16(tmem + COL_D, tmem + COL_AHI + ks * 8, bd, idesc16, (rep | ks) ? 1u : 0u);
                     }
-                if (p.terms >= 2)
-                    for (int ks = 0; ks < K / 8; ++ks) {       // tf32: 8 k per MMA = 8 TMEM columns, 32 B in the swizzle atom
-                        mma_ts_tf32(tmem + COL_D, tmem + COL_AHI + ks * 8, make_desc(Blo + (ks >> 2) * 2048) + (uint64_t)((ks & 3) * 2), idesc_tf32, acc);
-                        acc = 1;
-                    }
-                for (int ks = 0; ks < K / 8; ++ks) {
-                    mma_ts_tf32(tmem + COL_D, tmem + COL_AHI + ks * 8, make_desc(Bhi + (ks >> 2) * 2048) + (uint64_t)((ks & 3) * 2), idesc_tf32, acc);
-                    acc = 1;
+                    if (p.terms >= 3)
+                        for (int ks = 0; ks < K / 16; ++ks)
+                            mma_ts_f16(tmem + COL_D + N, tmem + COL_ALO + ks * 8, make_desc(B + (ks >> 2) * KB_BYTES) + (uint64_t)((ks & 3) * 2), idesc16, 1u);
                 }
                 commit(bar);
             }
@@ -205,10 +191,11 @@ __global__ void __launch_bounds__(NT, 1) step_kernel(const Params p)
             ok = mbar_wait_bounded(bar, (uint32_t)(s & 1));
             t2 = clock64();
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            float v[16];
+            float v[16], l[16];
             tmem_ld16(tmem + ((uint32_t)(warp * 32) << 16) + COL_D, v);
+            tmem_ld16(tmem + ((uint32_t)(warp * 32) << 16) + COL_D + N, l);
 #pragma unroll
-            for (int i = 0; i < 16; ++i) keep += v[i];
+            for (int i = 0; i < 16; ++i) { if (p.terms >= 2) v[i] = __fadd_rn(v[i], __fmul_rn(l[i], LO_UNSCALE)); keep += v[i]; }
             if (s == p.steps - 1 && blockIdx.x == 0) {
 #pragma unroll
                 for (int i = 0; i < 16; ++i) p.D[(size_t)(warp * 32 + lane) * N + i] = v[i];
@@ -234,55 +221,54 @@ __global__ void __launch_bounds__(NT, 1) step_kernel(const Params p)
 
 int main()
 {
-    std::vector<float> W((size_t)M * K), h((size_t)N * K);
-    srand(7);
-    for (auto &x : W) x = 0.2f * ((float)rand() / RAND_MAX - 0.5f);       // U(-0.1, 0.1): the reference's default initialisation
-    for (auto &x : h) x = 2.0f * ((float)rand() / RAND_MAX - 0.5f);       // layer outputs live in (-1, 1)
-    for (int n = 12; n < N; ++n) for (int k = 0; k < K; ++k) h[(size_t)n * K + k] = 0.0f;   // 12 sequences per CTA at C2, padded to 16
-    for (int m = 0; m < M; ++m) for (int k = 250; k < K; ++k) W[(size_t)m * K + k] = 0.0f;  // H = 250 padded to 256
-    std::vector<double> ref((size_t)M * N);
-    std::vector<float> ref32((size_t)M * N);
-    double refmax = 0;
-    for (int m = 0; m < M; ++m) for (int n = 0; n < N; ++n) {
-        double s = 0; float s32 = 0;
-        for (int k = 0; k < K; ++k) { s += (double)W[(size_t)m * K + k] * h[(size_t)n * K + k]; s32 = s32 + W[(size_t)m * K + k] * h[(size_t)n * K + k]; }
-        ref[(size_t)m * N + n] = s; ref32[(size_t)m * N + n] = s32; refmax = fmax(refmax, fabs(s));
-    }
-    double e32 = 0;
-    for (size_t i = 0; i < ref.size(); ++i) e32 = fmax(e32, fabs(ref32[i] - ref[i]));
-    printf("fp32 serial sum (the reference's own order) vs fp64: max err / max|ref| = %.3e\n", e32 / refmax);
-
     float *dW, *dh, *dD; long long *cyc; int *err;
-    cudaMalloc(&dW, W.size() * 4); cudaMalloc(&dh, h.size() * 4); cudaMalloc(&dD, (size_t)M * N * 4);
+    cudaMalloc(&dW, (size_t)M * K * 4); cudaMalloc(&dh, (size_t)N * K * 4); cudaMalloc(&dD, (size_t)M * N * 4);
     cudaMallocManaged(&cyc, 4 * sizeof(long long)); cudaMallocManaged(&err, sizeof(int));
-    cudaMemcpy(dW, W.data(), W.size() * 4, cudaMemcpyHostToDevice);
-    cudaMemcpy(dh, h.data(), h.size() * 4, cudaMemcpyHostToDevice);
-    const int smem = 2 * BHI_BYTES + BBF_BYTES + 64 + 1024;
+    const int smem = B_BYTES + 64 + 1024;
     cudaFuncSetAttribute(step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     int nsm = 0; cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, 0);
 
-    struct { int terms, low_even; const char *name; } cases[] = {
-        {1, 1, "W_hi*h_hi only (tf32)"}, {2, 1, "+ W_hi*h_lo (tf32)"},
-        {3, 1, "+ bf16(W_lo)*bf16(h) (low half = even k)"}, {3, 0, "+ bf16(W_lo)*bf16(h) (low half = odd k)"} };
-    for (auto &c : cases) {
-        Params p{dW, dh, dD, cyc, err, 1, c.terms, c.low_even};
-        *err = 0; cudaMemset(dD, 0xff, (size_t)M * N * 4);
-        step_kernel<<<1, NT, smem>>>(p);
-        cudaError_t e = cudaDeviceSynchronize();
-        std::vector<float> D((size_t)M * N);
-        cudaMemcpy(D.data(), dD, D.size() * 4, cudaMemcpyDeviceToHost);
-        double worst = 0;
-        for (size_t i = 0; i < D.size(); ++i) worst = fmax(worst, fabs((double)D[i] - ref[i]));
-        printf("%-48s max err / max|ref| = %.3e   (%s%s)\n", c.name, worst / refmax, cudaGetErrorString(e), *err ? ", mbarrier wait timed out" : "");
-        if (e != cudaSuccess) return 1;
+    // weight scales: the reference's default U(-0.1, 0.1), trained-size weights U(-3, 3), and tiny weights (fp16 subnormal hi parts)
+    for (float wscale : {0.1f, 3.0f, 1e-4f}) {
+        std::vector<float> W((size_t)M * K), h((size_t)N * K);
+        srand(7);
+        for (auto &x : W) x = 2.0f * wscale * ((float)rand() / RAND_MAX - 0.5f);
+        for (auto &x : h) x = 2.0f * ((float)rand() / RAND_MAX - 0.5f);       // layer outputs live in (-1, 1)
+        for (int n = 0; n < N; ++n) for (int k = 0; k < K; k += 7) h[(size_t)n * K + k] *= 1e-3f;   // some small outputs
+        for (int n = 12; n < N; ++n) for (int k = 0; k < K; ++k) h[(size_t)n * K + k] = 0.0f;
+        for (int m = 0; m < M; ++m) for (int k = 250; k < K; ++k) W[(size_t)m * K + k] = 0.0f;
+        std::vector<double> ref((size_t)M * N);
+        double refmax = 0, e32 = 0;
+        for (int m = 0; m < M; ++m) for (int n = 0; n < N; ++n) {
+            double s = 0; float s32 = 0;
+            for (int k = 0; k < K; ++k) { s += (double)W[(size_t)m * K + k] * h[(size_t)n * K + k]; s32 = s32 + W[(size_t)m * K + k] * h[(size_t)n * K + k]; }
+            ref[(size_t)m * N + n] = s; refmax = fmax(refmax, fabs(s)); e32 = fmax(e32, fabs((double)s32 - s));
+        }
+        printf("weights U(-%g, %g): fp32 serial sum (the reference's own order) vs fp64: max err / max|ref| = %.3e\n", wscale, wscale, e32 / refmax);
+        cudaMemcpy(dW, W.data(), W.size() * 4, cudaMemcpyHostToDevice);
+        cudaMemcpy(dh, h.data(), h.size() * 4, cudaMemcpyHostToDevice);
+        struct { int terms; const char *name; } cases[] = { {1, "W_hi*h_hi only (fp16)"}, {2, "+ W_hi*h_lo'"}, {3, "+ W_lo'*h_hi"} };
+        for (auto &c : cases) {
+            Params p{dW, dh, dD, cyc, err, 1, c.terms, 1};
+            *err = 0; cudaMemset(dD, 0xff, (size_t)M * N * 4);
+            step_kernel<<<1, NT, smem>>>(p);
+            cudaError_t e = cudaDeviceSynchronize();
+            std::vector<float> D((size_t)M * N);
+            cudaMemcpy(D.data(), dD, D.size() * 4, cudaMemcpyDeviceToHost);
+            double worst = 0;
+            for (size_t i = 0; i < D.size(); ++i) worst = fmax(worst, fabs((double)D[i] - ref[i]));
+            printf("  %-28s max err / max|ref| = %.3e   (%s%s)\n", c.name, worst / refmax, cudaGetErrorString(e), *err ? ", mbarrier wait timed out" : "");
+            if (e != cudaSuccess) return 1;
+        }
     }
-    for (int terms : {3, 1}) {
-        Params p{dW, dh, dD, cyc, err, 2000, terms, 1};
+    struct { int terms, nrep; const char *name; } tc[] = { {3, 1, "16 x N=32 + 16 x N=16"}, {3, 2, "2 x (16 x N=32 + 16 x N=16)"}, {2, 1, "16 x N=32"}, {2, 2, "32 x N=32"}, {1, 1, "16 x N=16"}, {1, 2, "32 x N=16"} };
+    for (auto &c : tc) {
+        Params p{dW, dh, dD, cyc, err, 2000, c.terms, c.nrep};
         *err = 0;
         step_kernel<<<nsm, NT, smem>>>(p);
         cudaError_t e = cudaDeviceSynchronize();
-        printf("%d CTAs x 2000 steps, %2d MMAs/step: %lld cycles/step = write B %lld + MMA issue..complete %lld + tcgen05.ld %lld + barrier  (%s%s)\n",
-               nsm, terms == 3 ? 80 : 32, cyc[0], cyc[1], cyc[2], cyc[3], cudaGetErrorString(e), *err ? ", mbarrier wait timed out" : "");
+        printf("%d CTAs x 2000 steps, MMAs/step %-28s: %lld cycles/step = write B %lld + MMA issue..complete %lld + tcgen05.ld %lld + barrier  (%s%s)\n",
+               nsm, c.name, cyc[0], cyc[1], cyc[2], cyc[3], cudaGetErrorString(e), *err ? ", mbarrier wait timed out" : "");
         if (e != cudaSuccess) return 1;
     }
     return 0;

@@ -1,5 +1,6 @@
-"""GPU tuning aid: per-phase cycle breakdown of the forward persistent kernel from in-kernel clock64 stamps.
-    BLSTM_REC_TRACE=1 [BLSTM_FWD_G=.. BLSTM_FWD_NSUB=..] python tools/trace_recurrent.py [H] [S] [T]"""
+"""GPU tuning aid: per-phase cycle breakdown of the persistent recurrent kernels from in-kernel clock64 stamps.
+    [BLSTM_REC_V=3] [BLSTM_FWD_G=..] python tools/trace_recurrent.py [H] [S] [T] [L = 2H bidirectional | u = unidirectional]
+tm2 kernels (default): forward and BPTT, 8 stamps per step; first tensor-memory generation / register kernels: forward only, 6 stamps."""
 import ctypes
 import os
 import sys
@@ -26,18 +27,47 @@ net = cb.Net(ctx, net_json, S, T)
 for i, w in enumerate(synth.init_weights(net_json, 2)):
     if len(w):
         net.set_weights(i, w)
-print("plan", net.plan_info(1))
+info = net.plan_info(1)
+print("plan", info)
 net.load_fraction(frac)
 for it in range(3):
     net.forward()
+    net.calculate_error()
+    net.backward()
 ctx.sync()
-buf = np.zeros((ctx.num_sms * 4, T, 6), np.int64)
+
+
+def show(d):
+    for name, v in d.items():
+        per_row = v.mean(1)
+        print("  %-34s mean %7.0f cyc   min-row %7.0f  max-row %7.0f  p99 %7.0f" % (name, v.mean(), per_row.min(), per_row.max(), np.percentile(v, 99)))
+
+
 rows = ctypes.c_int()
-h.cn_lstm_debug_trace.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.POINTER(ctypes.c_int)]
-assert h.cn_lstm_debug_trace(net.p, 1, T, buf.ctypes.data_as(ctypes.c_void_p), ctypes.byref(rows)) == 0, h.cn_last_error()
-tr = buf.reshape(-1)[: rows.value * T * 6].reshape(rows.value, T, 6)[:, 5:T - 1, :]      # skip the first steps and the last
-d = {"prefetch+wait": tr[:, :, 1] - tr[:, :, 0], "copy": tr[:, :, 2] - tr[:, :, 1], "gemm": tr[:, :, 3] - tr[:, :, 2],
-     "gate math+stores": tr[:, :, 4] - tr[:, :, 3], "publish": tr[:, :, 5] - tr[:, :, 4], "step": tr[:, 1:, 0] - tr[:, :-1, 0]}
-for name, v in d.items():
-    per_row = v.mean(1)
-    print("%-18s mean %8.0f cyc   min-row %8.0f  max-row %8.0f  p99 %8.0f" % (name, v.mean(), per_row.min(), per_row.max(), np.percentile(v, 99)))
+if info["fwd_kernel"] == "tm2":
+    h.cn_lstm_debug_trace2.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.POINTER(ctypes.c_int)]
+    for bwd in (0, 1):
+        buf = np.zeros((ctx.num_sms, T, 8), np.int64)
+        assert h.cn_lstm_debug_trace2(net.p, 1, bwd, T, buf.ctypes.data_as(ctypes.c_void_p), ctypes.byref(rows)) == 0, h.cn_last_error()
+        tr = buf.reshape(-1)[: rows.value * T * 8].reshape(rows.value, T, 8)[:, 5:T - 2, :]      # skip the first steps and the last
+        step = tr[:, 1:, 0] - tr[:, :-1, 0]
+        if not bwd:
+            print("forward (lstm_fwd_tm2_kernel), stamps of warp 0 + the control warp:")
+            d = {"loads issued + exchange polled": tr[:, :, 1] - tr[:, :, 0], "B tile written -> MMAs complete": tr[:, :, 2] - tr[:, :, 1],
+                 "tcgen05.ld + transpose + gate math": tr[:, :, 3] - tr[:, :, 2], "re-arm flag + h stored": tr[:, :, 4] - tr[:, :, 3],
+                 "result stores issued": tr[:, :, 5] - tr[:, :, 4], "control: step start -> MMAs issued": tr[:, :, 6] - tr[:, :, 0],
+                 "control: MMAs issued -> re-arm fenced": tr[:, :, 7] - tr[:, :, 6], "step": step}
+        else:
+            print("BPTT (lstm_bwd_tm2_kernel):")
+            d = {"loads issued + partials polled": tr[:, :, 1] - tr[:, :, 0], "delta math + B tile": tr[:, :, 2] - tr[:, :, 1],
+                 "result stores + MMAs complete": tr[:, :, 3] - tr[:, :, 2], "tcgen05.ld + flag + partials stored": tr[:, :, 4] - tr[:, :, 3],
+                 "control: step start -> MMAs issued": tr[:, :, 6] - tr[:, :, 0], "control: MMAs issued -> re-arm fenced": tr[:, :, 7] - tr[:, :, 6],
+                 "step": step}
+        show(d)
+else:
+    buf = np.zeros((ctx.num_sms * 4, T, 6), np.int64)
+    h.cn_lstm_debug_trace.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.POINTER(ctypes.c_int)]
+    assert h.cn_lstm_debug_trace(net.p, 1, T, buf.ctypes.data_as(ctypes.c_void_p), ctypes.byref(rows)) == 0, h.cn_last_error()
+    tr = buf.reshape(-1)[: rows.value * T * 6].reshape(rows.value, T, 6)[:, 5:T - 1, :]      # skip the first steps and the last
+    show({"prefetch+wait": tr[:, :, 1] - tr[:, :, 0], "copy": tr[:, :, 2] - tr[:, :, 1], "gemm": tr[:, :, 3] - tr[:, :, 2],
+          "gate math+stores": tr[:, :, 4] - tr[:, :, 3], "publish": tr[:, :, 5] - tr[:, :, 4], "step": tr[:, 1:, 0] - tr[:, :-1, 0]})
