@@ -90,6 +90,12 @@ int  bl_memcpy_d2d(bl_ctx *ctx, void *dst, const void *src, size_t bytes);
 /* strided row copies: `rows` rows of `row_bytes`, pitches in bytes (packed host <-> padded device) */
 int  bl_memcpy2d_h2d(bl_ctx *ctx, void *dst, size_t dst_pitch, const void *host_src, size_t src_pitch, size_t row_bytes, size_t rows);
 int  bl_memcpy2d_d2h(bl_ctx *ctx, void *host_dst, size_t dst_pitch, const void *src, size_t src_pitch, size_t row_bytes, size_t rows);
+/* Upload fence for pinned staging buffers: bl_upload_mark records a point in the context's stream (after the asynchronous H2D copies
+ * enqueued so far) and returns a ticket; bl_upload_wait blocks the host until that point has been reached (returns at once if it
+ * already has).  The fraction objects use it so that a pinned buffer never goes back to the staging pool while a copy out of it is
+ * still queued -- the reference's synchronous thrust::copy (layers/InputLayer.cpp:59) needs no such thing. */
+int  bl_upload_mark(bl_ctx *ctx, unsigned long long *ticket);
+int  bl_upload_wait(bl_ctx *ctx, unsigned long long ticket);
 /* pinned host memory for the fraction staging buffers */
 int  bl_malloc_host(bl_ctx *ctx, void **ptr, size_t bytes);
 int  bl_free_host(bl_ctx *ctx, void *ptr);

@@ -98,6 +98,8 @@ int bl_ctx_create(int device, void *stream, bl_ctx **out)
     ctx->scratch_bytes = 0;
     ctx->scratch2 = nullptr;
     ctx->scratch2_bytes = 0;
+    for (int i = 0; i < 8; ++i) { ctx->up_ev[i] = nullptr; ctx->up_ticket[i] = 0; }
+    ctx->up_next = 0;
     if (stream) { ctx->stream = (cudaStream_t)stream; ctx->own_stream = false; }
     else {
         if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess) {
@@ -116,6 +118,7 @@ void bl_ctx_destroy(bl_ctx *ctx)
     cudaStreamSynchronize(ctx->stream);
     if (ctx->scratch) cudaFree(ctx->scratch);
     if (ctx->scratch2) cudaFree(ctx->scratch2);
+    for (int i = 0; i < 8; ++i) if (ctx->up_ev[i]) cudaEventDestroy(ctx->up_ev[i]);
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -170,5 +173,26 @@ int bl_malloc_host(bl_ctx *ctx, void **ptr, size_t bytes)
     return 0;
 }
 int bl_free_host(bl_ctx *ctx, void *ptr) { if (ptr) BL_CUDA(ctx, cudaFreeHost(ptr)); return 0; }
+
+int bl_upload_mark(bl_ctx *ctx, unsigned long long *ticket)
+{
+    const unsigned long long t = ++ctx->up_next;
+    const int slot = (int)(t % 8);
+    if (!ctx->up_ev[slot]) BL_CUDA(ctx, cudaEventCreateWithFlags(&ctx->up_ev[slot], cudaEventDisableTiming));
+    else if (ctx->up_ticket[slot]) BL_CUDA(ctx, cudaEventSynchronize(ctx->up_ev[slot]));     // the ring wrapped: the old ticket is done after this
+    BL_CUDA(ctx, cudaEventRecord(ctx->up_ev[slot], ctx->stream));
+    ctx->up_ticket[slot] = t;
+    *ticket = t;
+    return 0;
+}
+
+int bl_upload_wait(bl_ctx *ctx, unsigned long long ticket)
+{
+    if (!ticket) return 0;
+    const int slot = (int)(ticket % 8);
+    if (ctx->up_ticket[slot] != ticket) return 0;      // slot reused: the ticket was waited for when it was overwritten
+    BL_CUDA(ctx, cudaEventSynchronize(ctx->up_ev[slot]));
+    return 0;
+}
 
 } // extern "C"

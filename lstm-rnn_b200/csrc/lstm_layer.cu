@@ -168,7 +168,7 @@ int bl_lstm_plan_create(bl_ctx *ctx, int P, int L, int bidirectional, int S, int
     rc |= bl_malloc(ctx, (void **)&pl->flags_b, (size_t)pl->ndir * pl->gb.G * 32 * sizeof(unsigned));
     if (getenv("BLSTM_REC_TRACE")) {
         rc |= bl_malloc(ctx, (void **)&pl->trace, (size_t)ctx->num_sms * 4 * maxT * 8 * sizeof(long long));
-        rc |= bl_malloc(ctx, (void **)&pl->trace_b, (size_t)ctx->num_sms * maxT * 8 * sizeof(long long));
+        rc |= bl_malloc(ctx, (void **)&pl->trace_b, (size_t)ctx->num_sms * 2 * maxT * 8 * sizeof(long long));
     }
     if (rc) { bl_lstm_plan_destroy(pl); return 1; }
     // zero-filled like the reference's buffers (LstmLayer.cu:554); the exchange buffers' padding columns must stay zero
@@ -195,11 +195,12 @@ void bl_lstm_plan_destroy(bl_lstm_plan *pl)
 int bl_lstm_plan_info(const bl_lstm_plan *pl, int *o)
 {
     // smem is a multiple of 4: the low two bits carry nsub (1, 2, 4 -> 1, 2, 0), or 3 for the register-resident kernels
-    // (the tensor-memory kernels report their smem rounded up to 16 with 11 (generation 1) or 13 (tm2) in the low four bits)
+    // (the tensor-memory kernels report their smem rounded up to 16 with 11 (generation 1) or 13 / 14 (tm2 with one / two sub-groups
+    // per CTA) in the low four bits)
     o[0] = pl->gf.G; o[1] = pl->gf.C; o[2] = pl->gf.CL;
-    o[3] = pl->t2_f ? (int)((pl->gf.smem + 15) & ~(size_t)15) + 13 : pl->tm_f ? (int)((pl->gf.smem + 15) & ~(size_t)15) + 11 : (int)pl->gf.smem + (pl->reg_f ? 3 : pl->gf.nsub);
+    o[3] = pl->t2_f ? (int)((pl->gf.smem + 15) & ~(size_t)15) + 12 + pl->gf.nsub : pl->tm_f ? (int)((pl->gf.smem + 15) & ~(size_t)15) + 11 : (int)pl->gf.smem + (pl->reg_f ? 3 : pl->gf.nsub);
     o[4] = pl->gb.G; o[5] = pl->gb.C; o[6] = pl->gb.CL;
-    o[7] = pl->t2_b ? (int)((pl->gb.smem + 15) & ~(size_t)15) + 13 : pl->tm_b ? (int)((pl->gb.smem + 15) & ~(size_t)15) + 11 : (int)pl->gb.smem + (pl->reg_b ? 3 : pl->gb.nsub);
+    o[7] = pl->t2_b ? (int)((pl->gb.smem + 15) & ~(size_t)15) + 12 + pl->gb.nsub : pl->tm_b ? (int)((pl->gb.smem + 15) & ~(size_t)15) + 11 : (int)pl->gb.smem + (pl->reg_b ? 3 : pl->gb.nsub);
     return 0;
 }
 
@@ -396,7 +397,7 @@ int bl_lstm_debug_trace2(bl_lstm_plan *pl, int backward, int T, long long *host_
     if (!src) return bl::fail(pl->ctx, "tracing is off (set BLSTM_REC_TRACE before creating the plan)");
     if (backward ? !pl->t2_b : !pl->t2_f) return bl::fail(pl->ctx, "bl_lstm_debug_trace2: the plan does not run the tm2 kernel for this pass");
     const bl::RecGeom &g = backward ? pl->gb : pl->gf;
-    const int n = pl->ndir * g.G * g.C;
+    const int n = pl->ndir * bl::cdiv(g.G, g.nsub) * g.C * g.nsub;       // one row per sub-group, CTA-major
     *rows = n;
     BL_CUDA(pl->ctx, cudaMemcpyAsync(host_dst, src, (size_t)n * T * 8 * sizeof(long long), cudaMemcpyDeviceToHost, pl->ctx->stream));
     BL_CUDA(pl->ctx, cudaStreamSynchronize(pl->ctx->stream));

@@ -283,12 +283,13 @@ __global__ void __launch_bounds__(RG_NT, 1) lstm_fwd_reg_kernel(const RecFwdPara
                     ig = __fadd_rn(ig, __fmul_rn(cprev[u], wpe[u][0]));
                     fg = __fadd_rn(fg, __fmul_rn(cprev[u], wpe[u][1]));
                 }
-                ni = tanh_fn_tab(ni, s_tab); ig = logistic_fn_tab(ig, s_tab); fg = logistic_fn_tab(fg, s_tab);
+                act3_tab(ni, ig, fg, s_tab, ni, ig, fg);        // the three first-level activations, interleaved
                 c = __fmul_rn(ni, ig);                            // :121-126
                 if (!first) c = __fadd_rn(c, __fmul_rn(cprev[u], fg));
                 og = __fadd_rn(og, __fmul_rn(c, wpe[u][2]));      // :129-131
-                og = logistic_fn_tab(og, s_tab);
-                h = __fmul_rn(tanh_fn_tab(c, s_tab), og);         // :134
+                float tc;
+                act2_tab(c, og, s_tab, tc, og);
+                h = __fmul_rn(tc, og);         // :134
                 r_ni[u] = ni; r_ig[u] = ig; r_fg[u] = fg; r_og[u] = og;
             }
             cprev[u] = c; r_h[u] = h;
@@ -425,7 +426,7 @@ __global__ void __launch_bounds__(RG_NT, 1) lstm_bwd_reg_kernel(const RecBwdPara
                 nfg[u] = 0.0f;
             } else {
                 const float ni = a[u][0], ig = a[u][1], fg = a[u][2], og = a[u][3];
-                const float tc = tanh_fn_tab(c[u], s_tab);
+                const float tc = tanh1_tab(c[u], s_tab);
                 dog = __fmul_rn(__fmul_rn(logistic_deriv(og), tc), e);                                   // :246
                 cerr = __fadd_rn(__fmul_rn(__fmul_rn(og, tanh_deriv(tc)), e), __fmul_rn(wpe[u][2], dog)); // :250
                 if (!firstCall)                                                                            // :252-262

@@ -22,8 +22,9 @@ public:
 
     // host buffers; pinned when the fraction was built with a device context.  Pinned blocks come from a process-wide
     // pool (cudaMallocHost / cudaFreeHost cost milliseconds and cudaFreeHost synchronises the device): a block goes back
-    // to the pool when its fraction dies.  That is safe because NeuralNetwork::calculateError() reads the error back
-    // (a stream synchronisation after the H2D copies of loadSequences) before a training step returns.
+    // to the pool when its fraction dies.  NeuralNetwork::loadSequences copies out of these buffers asynchronously and leaves an
+    // upload ticket with the fraction (noteUpload); the destructor waits for that point of the stream before the blocks are
+    // returned, so a forward-only caller that never synchronises cannot have a queued copy read a recycled block.
     struct PinnedPool {
         static void *get(bl_ctx *ctx, size_t bytes, size_t *capacity);
         static void put(void *ptr, size_t capacity);
@@ -51,6 +52,9 @@ public:
     };
 
     DataSetFraction() : m_inputPatternSize(0), m_outputPatternSize(0), m_maxSeqLength(0), m_minSeqLength(0), m_parallelSequences(0) {}
+    ~DataSetFraction() { if (m_uploadCtx) bl_upload_wait(m_uploadCtx, m_uploadTicket); }       // before the buffers go back to the pool
+    // called by NeuralNetwork::loadSequences after the last asynchronous H2D copy out of this fraction's buffers
+    void noteUpload(bl_ctx *ctx, unsigned long long ticket) const { m_uploadCtx = ctx; m_uploadTicket = ticket; }
 
     int inputPatternSize() const { return m_inputPatternSize; }
     int outputPatternSize() const { return m_outputPatternSize; }
@@ -82,6 +86,8 @@ private:
     HostBuffer<real_t> m_outputs;
     HostBuffer<char>   m_patTypes;
     HostBuffer<int>    m_targetClasses;
+    mutable bl_ctx *m_uploadCtx = nullptr;
+    mutable unsigned long long m_uploadTicket = 0;
 };
 
 } // namespace data_sets

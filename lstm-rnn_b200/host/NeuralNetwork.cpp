@@ -111,6 +111,10 @@ layers::PostOutputLayer &NeuralNetwork::postOutputLayer() { return static_cast<l
 void NeuralNetwork::loadSequences(const data_sets::DataSetFraction &fraction)
 {
     for (auto &layer : m_layers) layer->loadSequences(fraction);
+    // the copies out of the fraction's pinned buffers are asynchronous: leave a ticket so that the fraction outlives them
+    unsigned long long ticket = 0;
+    check(m_ctx, bl_upload_mark(m_ctx, &ticket));
+    fraction.noteUpload(m_ctx, ticket);
 }
 
 void NeuralNetwork::computeForwardPass()

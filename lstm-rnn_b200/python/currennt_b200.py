@@ -385,8 +385,9 @@ class Net:
         self._chk(self.h.cn_lstm_plan_info(self.p, i, out))
         d = dict(zip(("fwd_G", "fwd_C", "fwd_CL", "fwd_smem", "bwd_G", "bwd_C", "bwd_CL", "bwd_smem"), [int(x) for x in out]))
         for k in ("fwd", "bwd"):                      # the low two bits of the (4-byte aligned) smem size carry nsub (1, 2 or 4 -> 1, 2, 0)
-            if (d[k + "_smem"] & 15) in (11, 13):      # tensor-memory-resident kernels: generation 1 / tm2 (in-band exchange)
-                d[k + "_kernel"], d[k + "_nsub"] = ("tmem" if (d[k + "_smem"] & 15) == 11 else "tm2"), 1
+            if (d[k + "_smem"] & 15) in (11, 13, 14):  # tensor-memory-resident kernels: generation 1 / tm2 (in-band exchange) with 1 or 2 sub-groups
+                low = d[k + "_smem"] & 15
+                d[k + "_kernel"], d[k + "_nsub"] = ("tmem" if low == 11 else "tm2"), (1 if low == 11 else low - 12)
                 d[k + "_smem"] &= ~15
                 continue
             low = d[k + "_smem"] & 3

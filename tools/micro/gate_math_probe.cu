@@ -4,6 +4,7 @@
 //   0  exp_ref_tab as shipped (separately rounded double operations, table in shared memory)
 //   1  the same polynomial with fused multiply-adds (what glibc's FMA build of expf executes)
 //   2  variant 1 with the table lookup and scale done by integer ops on the result exponent (no 64-bit shared load)
+//   4  variant 0 with the activations of a level evaluated together in one basic block (act3_tab / act2_tab of common.cuh)
 //   3  fp32 __expf instead (NOT parity-safe: the floor of everything that is not the double-precision chain)
 //
 // nvcc -gencode arch=compute_100a,code=sm_100a -O3 -I../../lstm-rnn_b200/csrc -o gate_math_probe gate_math_probe.cu
@@ -75,11 +76,20 @@ __global__ void __launch_bounds__(512, 1) gate_kernel(const float *in, float *ou
         float fg = __fadd_rn(a2, __fmul_rn(h, 0.17f)), og = __fadd_rn(a3, __fmul_rn(h, 0.19f));
         ig = __fadd_rn(ig, __fmul_rn(c, wp0));
         fg = __fadd_rn(fg, __fmul_rn(c, wp1));
-        ni = th<V>(ni, s_tab); ig = sig<V>(ig, s_tab); fg = sig<V>(fg, s_tab);
-        c = __fadd_rn(__fmul_rn(ni, ig), __fmul_rn(c, fg));
-        og = __fadd_rn(og, __fmul_rn(c, wp2));
-        og = sig<V>(og, s_tab);
-        h = __fmul_rn(th<V>(c, s_tab), og);
+        if (V == 4) {                          // branch-free batches of common.cuh
+            act3_tab(ni, ig, fg, s_tab, ni, ig, fg);
+            c = __fadd_rn(__fmul_rn(ni, ig), __fmul_rn(c, fg));
+            og = __fadd_rn(og, __fmul_rn(c, wp2));
+            float tc;
+            act2_tab(c, og, s_tab, tc, og);
+            h = __fmul_rn(tc, og);
+        } else {
+            ni = th<V>(ni, s_tab); ig = sig<V>(ig, s_tab); fg = sig<V>(fg, s_tab);
+            c = __fadd_rn(__fmul_rn(ni, ig), __fmul_rn(c, fg));
+            og = __fadd_rn(og, __fmul_rn(c, wp2));
+            og = sig<V>(og, s_tab);
+            h = __fmul_rn(th<V>(c, s_tab), og);
+        }
         __syncthreads();                       // the real kernels have at least one CTA barrier per step
     }
     const long long t1 = clock64();
@@ -91,11 +101,13 @@ template <int V>
 static void run(const char *name, const float *in, float *out, long long *cyc, int nsm)
 {
     const int steps = 2000;
-    gate_kernel<V><<<nsm, 512>>>(in, out, cyc, steps);
-    cudaError_t e = cudaDeviceSynchronize();
-    long long lo = 1LL << 60, hi = 0;
-    for (int i = 0; i < nsm; ++i) { lo = cyc[i] < lo ? cyc[i] : lo; hi = cyc[i] > hi ? cyc[i] : hi; }
-    printf("%-70s %lld .. %lld cycles/step  (%s)\n", name, lo, hi, cudaGetErrorString(e));
+    for (int threads : {512, 256, 128, 32}) {
+        gate_kernel<V><<<nsm, threads>>>(in, out, cyc, steps);
+        cudaError_t e = cudaDeviceSynchronize();
+        long long lo = 1LL << 60, hi = 0;
+        for (int i = 0; i < nsm; ++i) { lo = cyc[i] < lo ? cyc[i] : lo; hi = cyc[i] > hi ? cyc[i] : hi; }
+        printf("%-70s %2d warps: %lld .. %lld cycles/step  (%s)\n", name, threads / 32, lo, hi, cudaGetErrorString(e));
+    }
 }
 
 int main()
@@ -105,8 +117,9 @@ int main()
     cudaMallocManaged(&in, (size_t)nsm * 512 * 4 * 4); cudaMallocManaged(&out, (size_t)nsm * 512 * 4); cudaMallocManaged(&cyc, nsm * 8);
     srand(3);
     for (size_t i = 0; i < (size_t)nsm * 512 * 4; ++i) in[i] = 2.0f * ((float)rand() / RAND_MAX - 0.5f);
-    run<0>("forward gate math, exp_ref_tab as shipped (5 double-precision exps)", in, out, cyc, nsm);
-    run<1>("same with fused multiply-adds in the polynomial", in, out, cyc, nsm);
+    run<0>("forward gate math, exp_ref_tab of common.cuh (glibc FMA form, 8 FP64 instructions per exp)", in, out, cyc, nsm);
+    run<1>("round-1 variant: fused polynomial only, z rounded separately (9 FP64 instructions)", in, out, cyc, nsm);
+    run<4>("branch-free batches (act3_tab / act2_tab): the three / two activations of a level interleave", in, out, cyc, nsm);
     run<3>("fp32 __expf instead of the double-precision chain (floor, not parity-safe)", in, out, cyc, nsm);
     // bit-agreement of the fused variant with the shipped one on this input set
     return 0;

@@ -47,21 +47,28 @@ rows = ctypes.c_int()
 if info["fwd_kernel"] == "tm2":
     h.cn_lstm_debug_trace2.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.POINTER(ctypes.c_int)]
     for bwd in (0, 1):
-        buf = np.zeros((ctx.num_sms, T, 8), np.int64)
+        buf = np.zeros((ctx.num_sms * 2, T, 8), np.int64)
         assert h.cn_lstm_debug_trace2(net.p, 1, bwd, T, buf.ctypes.data_as(ctypes.c_void_p), ctypes.byref(rows)) == 0, h.cn_last_error()
         tr = buf.reshape(-1)[: rows.value * T * 8].reshape(rows.value, T, 8)[:, 5:T - 2, :]      # skip the first steps and the last
+        nsub = info["bwd_nsub" if bwd else "fwd_nsub"]
+        if nsub == 2:           # rows are (CTA, sub-group): how far apart do the two sub-groups of a CTA run?
+            a, b = tr[0::2], tr[1::2]
+            ok = b[:, 0, 0] > 0                                               # idle second sub-groups record nothing
+            lag = (b[ok][:, :, 0] - a[ok][:, :, 0])
+            print("  sub-group 1 starts its step %.0f cycles after sub-group 0 (mean; min-row %.0f, max-row %.0f)" % (lag.mean(), lag.mean(1).min(), lag.mean(1).max()))
+            tr = a
         step = tr[:, 1:, 0] - tr[:, :-1, 0]
         if not bwd:
             print("forward (lstm_fwd_tm2_kernel), stamps of warp 0 + the control warp:")
             d = {"loads issued + exchange polled": tr[:, :, 1] - tr[:, :, 0], "B tile written -> MMAs complete": tr[:, :, 2] - tr[:, :, 1],
-                 "tcgen05.ld + transpose + gate math": tr[:, :, 3] - tr[:, :, 2], "re-arm flag + h stored": tr[:, :, 4] - tr[:, :, 3],
-                 "result stores issued": tr[:, :, 5] - tr[:, :, 4], "control: step start -> MMAs issued": tr[:, :, 6] - tr[:, :, 0],
-                 "control: MMAs issued -> re-arm fenced": tr[:, :, 7] - tr[:, :, 6], "step": step}
+                 "tcgen05.ld + transpose": tr[:, :, 3] - tr[:, :, 2], "gate math": tr[:, :, 4] - tr[:, :, 3],
+                 "exchange word stored": tr[:, :, 5] - tr[:, :, 4], "control: step start -> 1st K-block ready": tr[:, :, 6] - tr[:, :, 0],
+                 "control: 1st K-block -> MMAs issued": tr[:, :, 7] - tr[:, :, 6], "step": step}
         else:
             print("BPTT (lstm_bwd_tm2_kernel):")
             d = {"loads issued + partials polled": tr[:, :, 1] - tr[:, :, 0], "delta math + B tile": tr[:, :, 2] - tr[:, :, 1],
-                 "result stores + MMAs complete": tr[:, :, 3] - tr[:, :, 2], "tcgen05.ld + flag + partials stored": tr[:, :, 4] - tr[:, :, 3],
-                 "control: step start -> MMAs issued": tr[:, :, 6] - tr[:, :, 0], "control: MMAs issued -> re-arm fenced": tr[:, :, 7] - tr[:, :, 6],
+                 "result stores + MMAs complete": tr[:, :, 3] - tr[:, :, 2], "tcgen05.ld + partials stored": tr[:, :, 4] - tr[:, :, 3],
+                 "control: step start -> B tile ready": tr[:, :, 6] - tr[:, :, 0], "control: B tile ready -> MMAs issued": tr[:, :, 7] - tr[:, :, 6],
                  "step": step}
         show(d)
 else:
