@@ -49,11 +49,17 @@ WORKLOAD_SEED = {"C2": 2, "C3": 3, "C4": 4, "C5": 5}
 
 def peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    out = {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
     if os.path.exists(path):
         d = json.load(open(path))
-        return {"hbm_gbs": float(d["hbm_gbs"]), "bf16_tflops": float(d["bf16_tflops"]),
-                "bf16_tflops_sustained": float(d.get("bf16_tflops_sustained", d["bf16_tflops"])), "source": "measured"}
-    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
+        out = {"hbm_gbs": float(d["hbm_gbs"]), "bf16_tflops": float(d["bf16_tflops"]),
+               "bf16_tflops_sustained": float(d.get("bf16_tflops_sustained", d["bf16_tflops"])), "source": "measured"}
+    # dense TF32 peak measured by tools/measure_tf32_peak.py the way the driver measured bf16 (cuBLAS 8192^3, burst / 4 s sustained)
+    tpath = os.path.join(ROOT, "profiles", "r02_tf32_peak.json")
+    if os.path.exists(tpath):
+        t = json.load(open(tpath))
+        out.update(tf32_tflops=float(t["tf32_tflops"]), tf32_tflops_sustained=float(t["tf32_tflops_sustained"]))
+    return out
 
 
 class ClockSampler(threading.Thread):
@@ -329,6 +335,17 @@ def run_ours(args, rank, world, local_rank):
         class_ms, class_cnt = [float(x) for x in ms], [int(x) for x in cnt]
         k.bl_ctx_timing_enable(ctx.p, 0)
 
+    # data-parallel parity: after the same K steps every replica must hold bit-identical weights
+    dp_parity = None
+    if dist is not None:
+        import zlib
+        crc = [zlib.crc32(net.get_weights(i).tobytes()) for i in range(1, len(layer_shapes(net_json)) - 1)]
+        mine = torch.tensor(crc, dtype=torch.int64, device="cuda")
+        allc = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(allc, mine)
+        dp_parity = all(bool(torch.equal(allc[0], c)) for c in allc)
+        assert dp_parity, "data-parallel replicas diverged: weight checksums differ across ranks"
+
     tot = torch.tensor([float(frames), dev_ms, e2e_ms], dtype=torch.float64, device="cuda")
     if dist is not None:
         mx = tot.clone()
@@ -348,8 +365,12 @@ def run_ours(args, rank, world, local_rank):
         for i, nm in enumerate(names):
             d = {"ms_per_step": class_ms[i] / K, "launch_groups_per_step": class_cnt[i] / K, "share_of_kernel_time": share[i]}
             if nm == "gemm":
-                d.update(achieved_tflops=flops / (class_ms[i] * 1e-3) / 1e12 if class_ms[i] else None,
-                         frac_of_bf16_tensor_peak=(flops / (class_ms[i] * 1e-3) / 1e12) / pk["bf16_tflops_sustained"] if class_ms[i] else None)
+                tf = flops / (class_ms[i] * 1e-3) / 1e12 if class_ms[i] else None
+                d.update(achieved_tflops=tf, frac_of_bf16_tensor_peak=tf / pk["bf16_tflops_sustained"] if tf else None)
+                if tf and "tf32_tflops_sustained" in pk:
+                    # algorithmic flops against the measured dense TF32 peak; the strict mode issues 3 TF32 MMAs per useful one
+                    d.update(frac_of_tf32_tensor_peak=tf / pk["tf32_tflops_sustained"], tf32_issue_frac=(1.0 if args.mode == "fast" else 3.0) * tf / pk["tf32_tflops_sustained"],
+                             tf32_peak_tflops_sustained=pk["tf32_tflops_sustained"])
             if nm == "lstm_recurrent_fwd":
                 d.update(achieved_gbs=fwd_b / (class_ms[i] * 1e-3) / 1e9 if class_ms[i] else None)
             if nm == "lstm_bptt":
@@ -393,7 +414,19 @@ def run_ours(args, rank, world, local_rank):
                            "plan": plan},
                 "e2e": {"value": total_frames / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 8},
                 "device_ms_per_step": dev_ms / K, "gpu_launches": launches, "clocks": clocks, "roofline": roofline,
-                "kernel_classes": classes}
+                "kernel_classes": classes,
+                "notes": "value = fraction already resident in HBM when the timed region of a step starts (the bench contract); e2e = the "
+                         "same K steps through the host C ABI with pinned host buffers, H2D of the fraction and D2H of the objective inside "
+                         "the timed region -- the headline"}
+        if dp_parity is not None:
+            line["dp_parity"] = dp_parity
+            nw = sum(synth.layer_num_weights(t, L, P) for t, L, P in layer_shapes(net_json))
+            mode = os.environ.get("BLSTM_COMM_MODE", "overlap")
+            line["collective"] = {"kind": "ncclAllReduce(sum, fp32) of every layer's weightUpdates, in place", "bytes_per_step": 4 * nw,
+                                  "schedule": ("per layer on a side stream as soon as that layer's backward pass is enqueued, joined before the "
+                                               "weight update; communicator capped to %s CTAs (the SMs the persistent kernels leave free)"
+                                               % os.environ.get("BLSTM_COMM_MAX_CTAS", "4")) if mode != "grouped"
+                                  else "one grouped call after the whole backward pass"}
         if base:
             line["cpu_baseline"] = {kk: base[kk] for kk in ("value", "unit", "cores", "kind", "sample")}
             line["cpu_baseline"]["single_thread_value"] = single["value"]
@@ -409,7 +442,7 @@ def run_ours(args, rank, world, local_rank):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=40)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--mode", default="strict", choices=["strict", "fast"])

@@ -226,10 +226,14 @@ int  bl_comm_create(bl_ctx *ctx, int rank, int world, const void *id128, bl_comm
 void bl_comm_destroy(bl_comm *comm);
 /* rank / world size of the communicator (either pointer may be NULL) */
 void bl_comm_info(const bl_comm *comm, int *rank, int *world);
-/* In-place sum over ranks of `count` floats.  By default the request is queued and all queued buffers are reduced by one
- * grouped NCCL call in bl_comm_join (on the context's stream); with BLSTM_COMM_MODE=overlap it is issued at once on the
- * communicator's side stream, ordered after the work already enqueued on the context's stream.  Returns immediately. */
+/* In-place sum over ranks of `count` floats.  Default schedule (BLSTM_COMM_MODE unset or "overlap"): issued at once on the communicator's
+ * side stream, ordered after the work already enqueued on the context's stream, through a communicator capped to BLSTM_COMM_MAX_CTAS
+ * CTAs (default 4: the SMs the persistent recurrent kernels leave free), so that it overlaps with the backward pass of the layers
+ * below.  BLSTM_COMM_MODE=grouped: the request is queued and all queued buffers are reduced by one grouped NCCL call in
+ * bl_comm_join.  Returns immediately. */
 int  bl_allreduce_sum_f32(bl_comm *comm, float *buf, size_t count);
+/* The same for the LAST request before the join (nothing is left to overlap with): full-width communicator, context's stream. */
+int  bl_allreduce_sum_f32_last(bl_comm *comm, float *buf, size_t count);
 /* Completes (in stream order) every all-reduce requested so far: the buffers hold the sums for work enqueued afterwards. */
 int  bl_comm_join(bl_comm *comm);
 

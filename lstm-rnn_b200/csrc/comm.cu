@@ -1,11 +1,16 @@
 // Data-parallel gradient exchange: one NCCL communicator per process/GPU.  The reference has no
 // counterpart (single process, single GPU: currennt/src/main.cpp:526-541).
 //
-// Default schedule: bl_allreduce_sum_f32 only queues the buffer; bl_comm_join issues ONE grouped all-reduce of all queued
-// buffers on the compute stream.  Measured on B200: the persistent recurrent kernels occupy 144 of 148 SMs with one CTA
-// each, so an all-reduce launched on a side stream during the backward pass does not overlap -- it competes with the
-// cooperative launches for SMs (2 GPUs: 15.95 ms/step overlapped vs 15.58 ms grouped at the end, 15.33 ms single GPU).
-// BLSTM_COMM_MODE=overlap restores the per-layer side-stream schedule.
+// Two schedules (BLSTM_COMM_MODE):
+//   overlap  (default) bl_allreduce_sum_f32 issues the reduction at once on a side stream, ordered after the layer's backward pass, through
+//            a communicator split off with ncclConfig_t::maxCTAs = BLSTM_COMM_MAX_CTAS (default 4): the persistent recurrent kernels
+//            hold one CTA on each of 144 of the 148 SMs (cooperative launch, one tensor-memory allocation per SM), so an all-reduce
+//            only overlaps with the backward pass of the layers below if it fits the SMs they leave free -- uncapped (round 1) it took
+//            SMs the next cooperative launch then had to wait for.  The LAST gradient of a step (the first hidden layer's: nothing is
+//            left to hide it behind) goes through bl_allreduce_sum_f32_last: full-width communicator, compute stream.  bl_comm_join
+//            makes the compute stream wait for the side stream before the weight update.
+//   grouped  bl_allreduce_sum_f32 only queues the buffer; bl_comm_join issues ONE grouped all-reduce of all queued buffers on the
+//            compute stream.
 //
 // NCCL is resolved at run time with dlopen("libnccl.so.2"): inside a Python process that already imported torch
 // this binds to the NCCL torch loaded (one NCCL per process); in a plain C++ host it binds to the system library.
@@ -23,6 +28,7 @@ struct NcclApi {
     void *lib = nullptr;
     ncclResult_t (*GetUniqueId)(ncclUniqueId *) = nullptr;
     ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommSplit)(ncclComm_t, int, int, ncclComm_t *, ncclConfig_t *) = nullptr;                // NCCL >= 2.18; optional
     ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
     ncclResult_t (*GroupStart)() = nullptr;
@@ -47,6 +53,7 @@ int load_nccl(bl_ctx *ctx)
     BL_SYM(GroupEnd, "ncclGroupEnd")
     BL_SYM(GetErrorString, "ncclGetErrorString")
 #undef BL_SYM
+    *(void **)(&g_nccl.CommSplit) = dlsym(lib, "ncclCommSplit");
     g_nccl.lib = lib;
     return 0;
 }
@@ -54,12 +61,14 @@ int load_nccl(bl_ctx *ctx)
 
 struct bl_comm {
     bl_ctx      *ctx;
-    ncclComm_t   comm;
+    ncclComm_t   comm;                                          // full width: grouped mode, the last gradient of a step, statistics
+    ncclComm_t   side;                                          // overlap mode: capped to max_ctas CTAs (== comm when NCCL cannot split)
     cudaStream_t stream;
     cudaEvent_t  ready, done;
     int          rank, world;
     bool         pending;
-    bool         deferred;                                      // default: one grouped all-reduce at join time; BLSTM_COMM_MODE=overlap: per call, side stream
+    bool         deferred;                                      // BLSTM_COMM_MODE=grouped: one grouped all-reduce at join time; default: per call, side stream
+    int          max_ctas;
     std::vector<std::pair<float *, size_t>> queue;
 };
 
@@ -90,11 +99,20 @@ int bl_comm_create(bl_ctx *ctx, int rank, int world, const void *id128, bl_comm 
     BL_CUDA(ctx, cudaSetDevice(ctx->device));
     bl_comm *c = new bl_comm();
     c->ctx = ctx; c->rank = rank; c->world = world; c->pending = false;
-    { const char *m = getenv("BLSTM_COMM_MODE"); c->deferred = !(m && !strcmp(m, "overlap")); }
+    { const char *m = getenv("BLSTM_COMM_MODE"); c->deferred = (m && !strcmp(m, "grouped")); }
+    { const char *m = getenv("BLSTM_COMM_MAX_CTAS"); c->max_ctas = m ? atoi(m) : 4; }
     ncclUniqueId id;
     memcpy(&id, id128, sizeof(id));
     ncclResult_t r = g_nccl.CommInitRank(&c->comm, world, id, rank);
     if (r != ncclSuccess) { delete c; return bl::fail(ctx, "ncclCommInitRank failed: %s", g_nccl.GetErrorString(r)); }
+    c->side = c->comm;
+    if (!c->deferred && c->max_ctas > 0 && g_nccl.CommSplit) {
+        ncclConfig_t cfg = NCCL_CONFIG_INITIALIZER;
+        cfg.minCTAs = 1;
+        cfg.maxCTAs = c->max_ctas;          // stay inside the SMs the persistent recurrent kernels leave free
+        r = g_nccl.CommSplit(c->comm, 0, rank, &c->side, &cfg);
+        if (r != ncclSuccess) { g_nccl.CommDestroy(c->comm); delete c; return bl::fail(ctx, "ncclCommSplit failed: %s", g_nccl.GetErrorString(r)); }
+    }
     cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
     cudaEventCreateWithFlags(&c->ready, cudaEventDisableTiming);
     cudaEventCreateWithFlags(&c->done, cudaEventDisableTiming);
@@ -112,6 +130,8 @@ void bl_comm_destroy(bl_comm *c)
 {
     if (!c) return;
     cudaStreamSynchronize(c->stream);
+    cudaStreamSynchronize(c->ctx->stream);
+    if (c->side != c->comm) g_nccl.CommDestroy(c->side);
     g_nccl.CommDestroy(c->comm);
     cudaEventDestroy(c->ready); cudaEventDestroy(c->done);
     cudaStreamDestroy(c->stream);
@@ -126,9 +146,19 @@ int bl_allreduce_sum_f32(bl_comm *c, float *buf, size_t count)
     // the reduction may start once everything enqueued so far on the compute stream (the layer's backward) is done
     BL_CUDA(ctx, cudaEventRecord(c->ready, ctx->stream));
     BL_CUDA(ctx, cudaStreamWaitEvent(c->stream, c->ready, 0));
-    BL_NCCL(ctx, g_nccl.AllReduce(buf, buf, count, ncclFloat, ncclSum, c->comm, c->stream));
+    BL_NCCL(ctx, g_nccl.AllReduce(buf, buf, count, ncclFloat, ncclSum, c->side, c->stream));
     ctx->launches++;
     c->pending = true;
+    return 0;
+}
+
+int bl_allreduce_sum_f32_last(bl_comm *c, float *buf, size_t count)
+{
+    bl_ctx *ctx = c->ctx;
+    if (!count) return 0;
+    if (c->deferred) { c->queue.emplace_back(buf, count); c->pending = true; return 0; }
+    BL_NCCL(ctx, g_nccl.AllReduce(buf, buf, count, ncclFloat, ncclSum, c->comm, ctx->stream));
+    ctx->launches++;
     return 0;
 }
 

@@ -35,9 +35,10 @@
 namespace bl {
 
 // A CTA runs SUB = 1 or 2 independent SUB-GROUPS on the same weight slice: 16 / SUB gate-math warps and one control warp each, every
-// sub-group with its own sequence group (up to 16 / SUB sequences), B tile, accumulator columns and mbarriers.  With SUB = 2 one
-// sub-group's MMAs and gate math fill the other's exchange latency (the driver admits only ONE CTA per SM for a kernel that allocates
-// tensor memory -- tools/micro/occupancy_probe.cu -- so the interleaving has to happen inside the CTA).  Threads = (16 + SUB) * 32.
+// sub-group with its own sequence group (up to 16 / SUB sequences), B tile, accumulator columns and barriers -- an attempt to let one
+// sub-group's MMAs and gate math fill the other's exchange wait (the driver admits only ONE CTA per SM for a kernel that allocates
+// tensor memory, tools/micro/occupancy_probe.cu, so any interleaving has to happen inside the CTA).  Measured: no gain, the two drift to
+// a random relative phase; SUB = 2 stays as a tuning option (BLSTM_T2_SUB=2).  Threads = (16 + SUB) * 32.
 constexpr int T2_KB_MAX = 8;                     // K-blocks of 64 fp16: forward K = Hp <= 512
 constexpr int T2_MT_MAX = 4;                     // BPTT: 128-row tiles of source cells, R <= 512
 constexpr int T2_CMAX = 16;                      // BPTT: producers per (direction, group)
@@ -52,16 +53,16 @@ static int t2_pad(int x, int m) { return (x + m - 1) / m * m; }
 // ------------------------------------------------------------------------------------------------ geometry
 // RecGeom fields used: G (sequence groups = sub-groups), C, CL, SG, NT (= (16 + SUB) * 32), nsub (SUB: sub-groups per CTA), Hpad
 // (forward: K padded to 64; BPTT: R = source cells padded to 128), Spad (= 16 / SUB, the sequences a sub-group can hold), smem,
-// K4 (1: W_lo' lives in shared memory), RP (cycles the second sub-group starts behind the first), xelems (words of the exchange
-// buffer, all directions and both parities)
+// K4 (1: W_lo' lives in shared memory), RP / npair (tuning switches of the exchange poll), xelems (words of the exchange buffer, all
+// directions and both parities)
 bool choose_geometry_tm2(bool bwd, int H, int S, int ndir, int num_sms, int smem_cap, int forceG, RecGeom *out)
 {
     const int Hp = t2_pad(H, 64), R = t2_pad(H, 128);
     const char *es = getenv("BLSTM_T2_SUB");                     // tuning: sub-groups per CTA, 1 or 2 (default: whichever the model prefers)
     const int force_sub = es ? atoi(es) : 0;
-    const char *eg = getenv("BLSTM_T2_STAGGER");                 // tuning: cycles the second sub-group starts behind the first
-    const int stagger = eg ? atoi(eg) : 2300;
-    const char *ep = getenv("BLSTM_T2_POLL");                    // tuning: bit 0 early first poll, bit 1 re-poll all stale words at once, >> 2 = back-off ns
+    const char *eg = getenv("BLSTM_T2_POLL_DELAY");              // tuning: ns a warp sleeps between its exchange store and its first poll
+    const int poll_delay = eg ? atoi(eg) : 0;
+    const char *ep = getenv("BLSTM_T2_POLL");                    // tuning: bit 0 first poll ahead of the loop edge, bit 1 re-poll all stale words at once, >> 2 = back-off ns
     const int poll = ep ? atoi(ep) : 2;
     const int per_dir = num_sms / ndir;
     bool found = false;
@@ -101,14 +102,16 @@ bool choose_geometry_tm2(bool bwd, int H, int S, int ndir, int num_sms, int smem
                 // per step: the all-gather latency is the same for every split and a second sub-group hides most of it; the gate math
                 // is bound by the FP64 pipe, i.e. by the warps of the CTA that carry at least one (cell, sequence) pair
                 const int warps = SG * (G >= sub ? sub : 1);             // warp = sequence
-                const double chain = bwd ? 4200.0 : 4700.0, math = (bwd ? 45.0 : 130.0) * warps;
-                const double cost = (sub == 2 ? 0.6 * chain : chain) + math + 2.0 * C;
+                // (measured: two sub-groups drift to a random relative phase and gain nothing on C2 / C3 / C5 -- 5.13 k against 5.33 k cycles
+                // forward, 5.44 k against 5.32 k BPTT -- so a second sub-group is only used when asked for)
+                const double chain = bwd ? 4200.0 : 4200.0, math = (bwd ? 45.0 : 70.0) * warps;
+                const double cost = chain + (sub == 2 ? 100.0 : 0.0) + math + 2.0 * C;
                 if (!found || cost < best.cost) {
                     found = true;
                     best = RecGeom{};
                     best.G = G; best.C = C; best.CL = CL; best.SG = SG; best.NT = (16 + sub) * 32; best.nsub = sub; best.npair = poll;
                     best.R = bwd ? R : 128; best.Hpad = bwd ? R : Hp; best.RS = bwd ? R : Hp; best.Spad = NS; best.smem = smem; best.cost = cost;
-                    best.K4 = lo_smem; best.RP = stagger;
+                    best.K4 = lo_smem; best.RP = poll_delay;
                     best.xelems = bwd ? (size_t)ndir * 2 * G * C * NS * R : (size_t)ndir * 2 * S * Hp;
                 }
             }
@@ -356,10 +359,6 @@ __global__ void __maxnreg__(96) lstm_fwd_tm2_kernel(const RecFwdParams p)
     unsigned *xd = reinterpret_cast<unsigned *>(p.hx) + (size_t)d * 2 * xbuf;
     long long *trb = p.trace ? p.trace + ((size_t)blockIdx.x * SUB + sub) * T * 8 : nullptr;      // one row per sub-group
 
-    // Two sub-groups that start together stay together (equal periods, the FP64 pipe shared fairly: nothing pushes them apart) and
-    // collide in every phase; started half a period apart they stay apart, and one's MMAs and gate math fill the other's exchange wait
-    if (SUB == 2 && sub == 1) { const long long t0 = clock64(); while (clock64() - t0 < g.RP) { } }
-
     if (!active) {
         // idle sub-group: nothing to do until the teardown barrier
     } else if (ctrl) {
@@ -458,6 +457,7 @@ __global__ void __maxnreg__(96) lstm_fwd_tm2_kernel(const RecFwdParams p)
                 const unsigned *xs = xd + (size_t)((q - 1) & 1) * xbuf + (size_t)(s0 + prow) * Hp + pf4 * 4;
                 const unsigned want = (((q - 1) >> 1) & 1) ? T2_FTAG : 0u;        // tag of step q-1
                 if (!(px & 1)) {                                     // tuning: first poll here instead of at the end of the previous step
+                    if (g.RP > 0) __nanosleep(g.RP);                  // tuning: give the other producers' words time to land before the first poll
 #pragma unroll
                     for (int u = 0; u < T2_KB_MAX / 2; ++u) {
                         const int kb = ph + 2 * u;
@@ -680,8 +680,6 @@ __global__ void __maxnreg__(96) lstm_bwd_tm2_kernel(const RecBwdParams p)
     unsigned *exd = reinterpret_cast<unsigned *>(p.dx) + (size_t)d * 2 * ex_par + (size_t)grp * g.C * ex_slice;      // this group's C blocks, parity 0
     long long *trb = p.trace ? p.trace + ((size_t)blockIdx.x * SUB + sub) * T * 8 : nullptr;
 
-    if (SUB == 2 && sub == 1) { const long long t0 = clock64(); while (clock64() - t0 < g.RP) { } }      // half a period behind, see the forward kernel
-
     if (!active) {
         // idle sub-group
     } else if (ctrl) {
@@ -722,8 +720,12 @@ __global__ void __maxnreg__(96) lstm_bwd_tm2_kernel(const RecBwdParams p)
 #pragma unroll
             for (int gi = 0; gi < 3; ++gi) wpe[gi] = __ldg(p.Wp + gi * L + col);
         }
-        const int qd = lw & 3, sgp = lw >> 2;                       // epilogue: TMEM quadrant (== warp & 3) and sequence quad of this warp
-        const uint32_t tm_lane = tmem + ((uint32_t)(qd * 32) << 16) + col_d + 4 * sgp;
+        // epilogue: TMEM quadrant qd (== warp & 3), sequence octet soct, first tile tile0 of this warp: the sub-group's warps cover two
+        // tiles at a time with x8 loads (the tensor-memory port moves 64 B per cycle plus ~8 cycles per tcgen05.ld: 32 loads per step
+        // here against 64 with x4 loads)
+        constexpr int NOCT = NS / 8;
+        const int qd = lw & 3, soct = (lw >> 2) % NOCT, tile0 = lw / (4 * NOCT);
+        const uint32_t tm_lane = tmem + ((uint32_t)(qd * 32) << 16) + col_d + 8 * soct;
 
         for (int q = 0; q < T; ++q) {
             const int t = (d == 0) ? T - 1 - q : q;                 // fw walks time backwards, bw forwards (:936, :970)
@@ -838,25 +840,27 @@ __global__ void __maxnreg__(96) lstm_bwd_tm2_kernel(const RecBwdParams p)
                 unsigned *ex_w = exd + (size_t)(q & 1) * ex_par + (size_t)cs * ex_slice;
                 const unsigned tag = (q >> 1) & 1;
 #pragma unroll
-                for (int mt = 0; mt < MTMAX; ++mt)
+                for (int k = 0; k < (MTMAX + 1) / 2; ++k) {
+                    const int mt = tile0 + 2 * k;
                     if (mt < MT) {
-                        uint32_t r0[4], r1[4];
-                        t2_ld4(tm_lane + mt * 2 * NS, r0);
-                        t2_ld4(tm_lane + mt * 2 * NS + NS, r1);
+                        uint32_t r0[8], r1[8];
+                        t2_ld8(tm_lane + mt * 2 * NS, r0);
+                        t2_ld8(tm_lane + mt * 2 * NS + NS, r1);
                         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
                         const int ksrc = mt * 128 + qd * 32 + lane;
                         if (ksrc < H4) {
 #pragma unroll
-                            for (int i = 0; i < 4; ++i)
-                                if (4 * sgp + i < nseq) {
+                            for (int i = 0; i < 8; ++i)
+                                if (8 * soct + i < nseq) {
                                     const float o = __fmul_rn(__fmaf_rn(__uint_as_float(r1[i]), T2_LO_UNSCALE, __uint_as_float(r0[i])), wunscale);
                                     // last mantissa bit rounded away (nearest even; inf / NaN keep their class), then the tag
                                     const unsigned bb = __float_as_uint(o);
                                     const unsigned rr = ((bb & 0x7F800000u) == 0x7F800000u) ? (bb & ~1u) : ((bb + ((bb >> 1) & 1u)) & ~1u);
-                                    ex_w[(size_t)(4 * sgp + i) * R + ksrc] = rr | tag;
+                                    ex_w[(size_t)(8 * soct + i) * R + ksrc] = rr | tag;
                                 }
                         }
                     }
+                }
                 asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
                 if (tr) tr[4] = clock64();
             }

@@ -124,12 +124,21 @@ void NeuralNetwork::computeForwardPass()
 
 void NeuralNetwork::computeBackwardPass()
 {
+    // the trainable layer whose backward pass runs last: its gradient has nothing left to overlap with
+    const layers::Layer *lastReduced = nullptr;
+    if (m_comm)
+        for (auto &layer : m_layers) {
+            layers::TrainableLayer *tl = dynamic_cast<layers::TrainableLayer *>(layer.get());
+            if (tl && !tl->weightUpdates().empty()) { lastReduced = layer.get(); break; }
+        }
     for (auto it = m_layers.rbegin(); it != m_layers.rend(); ++it) {
         (*it)->computeBackwardPass();
         if (m_comm) {
             layers::TrainableLayer *tl = dynamic_cast<layers::TrainableLayer *>(it->get());
-            if (tl && !tl->weightUpdates().empty())
-                check(m_ctx, bl_allreduce_sum_f32(m_comm, tl->weightUpdates().data(), tl->weightUpdates().size()));
+            if (tl && !tl->weightUpdates().empty()) {
+                if (it->get() == lastReduced) check(m_ctx, bl_allreduce_sum_f32_last(m_comm, tl->weightUpdates().data(), tl->weightUpdates().size()));
+                else check(m_ctx, bl_allreduce_sum_f32(m_comm, tl->weightUpdates().data(), tl->weightUpdates().size()));
+            }
         }
     }
 }
