@@ -13,6 +13,7 @@
 // and the output errors dY [N][L] are read directly (no ResortOutputErrorsFn pass, :163-188).
 #include "lstm_recurrent.cuh"
 #include "gemm_tc.cuh"
+#include <algorithm>
 #include <cstdint>
 #include <cstdlib>
 
@@ -84,7 +85,9 @@ __global__ void lstm_small_grads_kernel(int N, int S, int H, int L, float bias, 
     }
 }
 
-__global__ void lstm_small_grads_finish_kernel(int L, int nsplit, const float *__restrict__ part,
+// bias_scale: 1 when the partials already carry the bias factor (lstm_small_grads_kernel), the layer's bias when they are plain delta
+// sums (accumulated inside lstm_bwd_tm2_kernel)
+__global__ void lstm_small_grads_finish_kernel(int L, int nsplit, float bias_scale, const float *__restrict__ part,
                                                float *__restrict__ dWbias, float *__restrict__ dWpeep)
 {
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
@@ -92,7 +95,7 @@ __global__ void lstm_small_grads_finish_kernel(int L, int nsplit, const float *_
     const int i = idx / L, col = idx % L;
     float s = 0.0f;
     for (int z = 0; z < nsplit; ++z) s += part[((size_t)z * 7 + i) * L + col];
-    if (i < 4) dWbias[i * L + col] = s;          // bias block: g*L + d*H + j
+    if (i < 4) dWbias[i * L + col] = bias_scale * s;          // bias block: g*L + d*H + j
     else       dWpeep[(i - 4) * L + col] = s;    // peephole block: q*L + d*H + j
 }
 
@@ -155,7 +158,7 @@ int bl_lstm_plan_create(bl_ctx *ctx, int P, int L, int bidirectional, int S, int
     const size_t N = (size_t)maxT * S;
     const size_t hx_elems = pl->t2_f ? pl->gf.xelems : (size_t)pl->ndir * 2 * S * pl->gf.RS;
     const size_t dx_elems = pl->t2_b ? pl->gb.xelems : (size_t)pl->ndir * 2 * S * pl->gb.RS;
-    pl->gsplit = 64;
+    pl->gsplit = std::max(64, pl->gb.G);
     int rc = 0;
     rc |= bl_malloc(ctx, (void **)&pl->acts, N * 4 * L * sizeof(float));
     rc |= bl_malloc(ctx, (void **)&pl->deltas, N * 4 * L * sizeof(float));
@@ -292,6 +295,7 @@ int bl_lstm_backward(bl_lstm_plan *pl, const float *W, const float *X, int ldx, 
     const bool tc = bl::tc_wanted(ctx, P, 4 * L, N);
     const bool fused_dsplit = tc && (pl->reg_b || pl->tm_b || pl->t2_b) && !pl->no_fused_split;
     p.ds_hi = p.ds_lo = nullptr; p.ld_ds = 0; p.trace = pl->trace_b;
+    p.gpart = pl->t2_b ? pl->gpart : nullptr;       // the tm2 BPTT kernel accumulates the bias / peephole gradient sums itself
     if (fused_dsplit) {
         BL_CHECK(plan_tc_buffers(pl));
         p.ds_hi = pl->tc_D; p.ds_lo = pl->tc_D + pl->tc_eD; p.ld_ds = (int)bl::tc_operand_ld(4 * pl->ndir * ((H + 3) & ~3));
@@ -363,17 +367,21 @@ int bl_lstm_backward(bl_lstm_plan *pl, const float *W, const float *X, int ldx, 
             }
     }
 
-    // (5) bias + peephole gradients
+    // (5) bias + peephole gradients: one block of partial sums per sequence group from the tm2 BPTT kernel, else a pass over the
+    //     deltas and cell states
     {
         bl::TimedRegion timed(ctx, 3);
-        int nsplit = pl->gsplit;
-        int rows = bl::cdiv(N, nsplit);
-        if (rows < 64) rows = 64;
-        nsplit = bl::cdiv(N, rows);
-        dim3 grid(bl::cdiv(L, 32), nsplit), block(32, 8);
-        bl::lstm_small_grads_kernel<<<grid, block, 0, ctx->stream>>>(N, S, H, L, pl->bias, pl->deltas, pl->cst, pl->gpart, rows);
-        BL_LAUNCHED(ctx);
-        bl::lstm_small_grads_finish_kernel<<<bl::cdiv(7 * L, 256), 256, 0, ctx->stream>>>(L, nsplit, pl->gpart, dWbias, dWpeep);
+        int nsplit = pl->gb.G;
+        if (!pl->t2_b) {
+            nsplit = pl->gsplit;
+            int rows = bl::cdiv(N, nsplit);
+            if (rows < 64) rows = 64;
+            nsplit = bl::cdiv(N, rows);
+            dim3 grid(bl::cdiv(L, 32), nsplit), block(32, 8);
+            bl::lstm_small_grads_kernel<<<grid, block, 0, ctx->stream>>>(N, S, H, L, pl->bias, pl->deltas, pl->cst, pl->gpart, rows);
+            BL_LAUNCHED(ctx);
+        }
+        bl::lstm_small_grads_finish_kernel<<<bl::cdiv(7 * L, 256), 256, 0, ctx->stream>>>(L, nsplit, pl->t2_b ? pl->bias : 1.0f, pl->gpart, dWbias, dWpeep);
         BL_LAUNCHED(ctx);
     }
     return 0;

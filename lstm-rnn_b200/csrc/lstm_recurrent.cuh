@@ -62,6 +62,10 @@ struct RecBwdParams {
     // optional (register-resident kernels only): TF32 split of the deltas, hi/lo [N][ld_ds], column (gate*ndir + d)*Hq + j
     float *ds_hi, *ds_lo; int ld_ds;
     long long *trace;               // optional [CTAs][T][8] clock64 stamps (tm2 kernels, BLSTM_REC_TRACE), else NULL
+    // tm2 kernel only: bias / peephole gradient partials accumulated in registers over the pass, one block per sequence group:
+    // gpart[group][7][L] = sum delta_ni, delta_ig, delta_fg, delta_og (bias, before the bias factor), sum c_prev*delta_ig,
+    // sum c_prev*delta_fg, sum c*delta_og (LstmLayer.cu:392-408, 440-475); NULL = not wanted
+    float *gpart;
     RecGeom g;
 };
 

@@ -46,6 +46,7 @@ constexpr unsigned T2_FTAG = 1u << 30;           // forward exchange word = fp16
 constexpr int T2_FWD_INIT = 0x40, T2_BWD_INIT = 0x01;   // cudaMemset bytes that give every word tag 1 (the first two steps carry tag 0)
 constexpr int T2_SPIN = 1 << 22;                 // polls before a kernel gives up and traps (a protocol bug must not hang the GPU)
 constexpr float T2_LO_SCALE = 2048.0f, T2_LO_UNSCALE = 1.0f / 2048.0f;
+constexpr float T2_DELTA_SCALE = 8192.0f;        // BPTT B operand: power-of-two scale of the gate deltas (undone with the weight scale)
 constexpr size_t T2_MIN_SMEM = 120 * 1024;       // more than half an SM: exactly one CTA (one 512-column TMEM allocation) per SM
 
 static int t2_pad(int x, int m) { return (x + m - 1) / m * m; }
@@ -638,7 +639,7 @@ __global__ void __maxnreg__(96) lstm_bwd_tm2_kernel(const RecBwdParams p)
         const int gate = idx / (ncell * H), rem = idx - gate * ncell * H;
         wmax = fmaxf(wmax, fabsf(__ldg(Wd + (size_t)gate * L * H + (size_t)j0 * H + rem)));
     }
-    const float wscale = t2_slice_scale(wmax, s_red, NT / 32), wunscale = __frcp_rn(wscale);
+    const float wscale = t2_slice_scale(wmax, s_red, NT / 32), wunscale = __fmul_rn(__frcp_rn(wscale), 1.0f / T2_DELTA_SCALE);
     for (int mt = 0; mt < MT; ++mt)
         for (int half = 0; half < 2; ++half) {
             for (int idx = tid; idx < 64 * 128; idx += NT) {
@@ -715,6 +716,7 @@ __global__ void __maxnreg__(96) lstm_bwd_tm2_kernel(const RecBwdParams p)
         const int slot = s0 + seq;
         float wpe[3] = {0, 0, 0};
         float nfg = 0.0f, ncerr = 0.0f, ndig = 0.0f, ndfg = 0.0f;  // "next step" state, :253-256
+        float gacc[7] = {0, 0, 0, 0, 0, 0, 0};                      // bias (4 gates) and peephole (ig, fg, og) gradient sums of this (cell, sequence)
         if (valid) {
             const int col = d * H + j0 + cell;
 #pragma unroll
@@ -798,8 +800,10 @@ __global__ void __maxnreg__(96) lstm_bwd_tm2_kernel(const RecBwdParams p)
                     const float dv[4] = {dni, dig, dfg, dog};
 #pragma unroll
                     for (int gi = 0; gi < 4; ++gi) {
+                        // |delta| <= 1 (limitedError): 2^13 keeps the fp16 halves of small deltas (deep layers: 1e-7) in the normal range;
+                        // unscaled, fp16's 5-bit exponent would put an ABSOLUTE floor of 1.5e-11 under every delta
                         uint32_t hi, lo;
-                        t2_split(dv[gi], hi, lo);
+                        t2_split(__fmul_rn(dv[gi], T2_DELTA_SCALE), hi, lo);
                         uint8_t *dst = Bt + (gi >> 1) * KBB + t2_off(seq, (gi & 1) * 32 + cell);
                         *reinterpret_cast<unsigned short *>(dst) = (unsigned short)hi;
                         *reinterpret_cast<unsigned short *>(dst + NS * 128) = (unsigned short)lo;      // row + NS
@@ -815,6 +819,11 @@ __global__ void __maxnreg__(96) lstm_bwd_tm2_kernel(const RecBwdParams p)
             if (tr) tr[2] = clock64();
             // ---- HBM-only results while the tensor pipe works
             if (valid) {
+                // the non-GEMM part of ComputeWeightUpdateFn (:392-408, 440-475): bias sums, peephole sums (ig / fg pair the delta with
+                // the cell state of the previous timestep of the direction, og with this timestep's)
+                gacc[0] = __fadd_rn(gacc[0], dni); gacc[1] = __fadd_rn(gacc[1], dig); gacc[2] = __fadd_rn(gacc[2], dfg); gacc[3] = __fadd_rn(gacc[3], dog);
+                if (!lastCall) { gacc[4] = __fmaf_rn(cp, dig, gacc[4]); gacc[5] = __fmaf_rn(cp, dfg, gacc[5]); }
+                gacc[6] = __fmaf_rn(c, dog, gacc[6]);
                 if (inplace) p.dY[row * p.lddy + d * H + j0 + cell] = e;    // unidirectional: tmpOutputErrors IS outputErrors (:907-910)
                 float *dp = p.deltas + row * 4 * L + d * H + j0 + cell;
                 dp[0] = dni; dp[L] = dig; dp[2 * L] = dfg; dp[3 * L] = dog;
@@ -863,6 +872,18 @@ __global__ void __maxnreg__(96) lstm_bwd_tm2_kernel(const RecBwdParams p)
                 }
                 asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
                 if (tr) tr[4] = clock64();
+            }
+        }
+        if (p.gpart) {
+            // sum the sub-group's sequences in order (deterministic) through the prologue's staging area, one block per sequence group
+            float *red = stage + (size_t)sub * 7 * NS * 32;
+#pragma unroll
+            for (int i = 0; i < 7; ++i) red[(i * NS + seq) * 32 + cell] = valid ? gacc[i] : 0.0f;
+            t2_named_barrier(1 + sub, GW * 32);
+            if (lw < 7 && cell < ncell) {
+                float sum = 0.0f;
+                for (int n = 0; n < nseq; ++n) sum = __fadd_rn(sum, red[(lw * NS + n) * 32 + cell]);
+                p.gpart[((size_t)grp * 7 + lw) * L + d * H + j0 + cell] = sum;
             }
         }
     }
