@@ -69,8 +69,10 @@ void JsonValue::write(std::string &out, bool pretty, int indent) const
         case Bool: out += m_bool ? "true" : "false"; break;
         case Number: {
             char buf[64];
+            // the reference's writer prints 6 significant digits ("%g"), which does not round-trip an fp32 weight; 9 digits do, and
+            // the reference's reader parses them unchanged (tests/test_gpu_weightfile.py feeds this output to it)
             if (m_isInt) snprintf(buf, sizeof(buf), "%d", (int)m_num);
-            else snprintf(buf, sizeof(buf), "%g", m_num);
+            else snprintf(buf, sizeof(buf), "%.9g", m_num);
             out += buf;
             break;
         }

@@ -38,8 +38,24 @@ CASES = {
 }
 
 
+def weight_file_fixture():
+    """The reference's own shipped network file (tests/test1/network.jsn: layers + trained weights, 6-digit decimals) as read by
+    the reference's own reader (rapidjson + TrainableLayer ctor, TrainableLayer.cu:65-101): the text and what it parsed to."""
+    path = os.path.join(HERE, "weightfile_test1.npz")
+    if os.path.exists(path) and "--all" not in sys.argv:
+        return
+    text = open("/root/reference/tests/test1/network.jsn").read()
+    ref = pyoracle.RefNet(text, 10, 8)
+    out = {"net_json": np.frombuffer(text.encode(), np.uint8), "types": np.array(ref.types), "sizes": np.array(ref.sizes)}
+    for i in range(ref.num_layers):
+        out["w%d" % i] = ref.get_weights(i)
+    np.savez_compressed(path, **out)
+    print("weightfile_test1", ref.types, [len(out["w%d" % i]) for i in range(ref.num_layers)])
+
+
 def main():
     pyoracle.build(ref=True)
+    weight_file_fixture()
     for name, (net_json, S, lengths, classes, tsize, seed) in CASES.items():
         if os.path.exists(os.path.join(HERE, name + ".npz")) and "--all" not in sys.argv:
             continue                                   # committed fixtures are only rewritten on request

@@ -159,6 +159,75 @@ def test_cli_forward_pass_single_csv(oracle, tmp_path):
             k += 1
 
 
+def _oracle_outputs(oracle, cfg, val, weights, S):
+    """Posteriors of every validation sequence from the oracle: list of [len][51] arrays in data-set order."""
+    vx, vc = val
+    net = oracle.OracleNet(cfg["net"], S, max(len(x) for x in vx))
+    for i, w in enumerate(weights):
+        if len(w):
+            net.set_weights(i, w)
+    out = []
+    for first in range(0, len(vx), S):
+        f = oracle.make_fraction(vx, S, first, seq_classes=vc, O=51)
+        net.load_fraction(f); net.forward()
+        y = net.get_outputs(len(json.loads(cfg["net"])["layers"]) - 2).reshape(f.T, S, 51)
+        for s in range(f.num_seqs):
+            out.append(y[:len(vx[first + s]), s].copy())
+    return out
+
+
+def _lagged(y, lag):
+    """main.cpp:345-349: row t shows the output of t + lag, the last `lag` rows repeat the final output."""
+    T = len(y)
+    return np.stack([y[t + lag] if t < T - lag else y[T - 1] for t in range(T)])
+
+
+@pytest.mark.parametrize("lag", [0, 2])
+def test_cli_forward_pass_csv_one_file_per_sequence(oracle, tmp_path, lag):
+    """ff_output_format = csv (currennt/src/main.cpp:368-420): one <tag>.csv per sequence under the output directory, one line per
+    timestep, outputs separated by ';' without a leading tag, ostream's 6 significant digits; --output_time_lag shifts the rows."""
+    cfg, train, val, weights = _setup(tmp_path)
+    _run(["--network", "network.jsn", "--ff_input_file", "val.nc", "--ff_output_file", "ffdir", "--ff_output_format", "csv",
+          "--parallel_sequences", "3", "--revert_std", "false", "--output_time_lag", str(lag)], str(tmp_path))
+    want = _oracle_outputs(oracle, cfg, val, weights, 3)
+    files = sorted(os.listdir(tmp_path / "ffdir"))
+    assert files == ["seq%03d.csv" % k for k in range(len(want))]
+    for k, y in enumerate(want):
+        text = open(tmp_path / "ffdir" / ("seq%03d.csv" % k)).read()
+        assert text.endswith("\n") and ";;" not in text
+        lines = text.splitlines()
+        assert len(lines) == len(y) and all(not ln.startswith(";") and ln.count(";") == 50 for ln in lines)
+        got = np.array([[float(v) for v in ln.split(";")] for ln in lines], np.float32)
+        assert np.allclose(got, _lagged(y, lag), rtol=2e-5, atol=1e-9)
+        # the text itself: every number printed like C++'s operator<<(float) does, i.e. "%g" of the fp32 value widened to double
+        first = lines[0].split(";")
+        assert first == ["%g" % float(np.float32(float(v))) for v in first]
+
+
+def test_cli_forward_pass_htk_files(oracle, tmp_path):
+    """ff_output_format = htk (currennt/src/main.cpp:430-478): per sequence <tag>.htk = big-endian HTK header {nSamples u32,
+    samplePeriod u32 = feature_period * 1e4, sampleSize u16 = 4 * outputs, parameterKind u16 = ff_output_kind} followed by
+    big-endian float32 rows.  Header bytes must be exact; the payload must be the posteriors."""
+    import struct
+    cfg, train, val, weights = _setup(tmp_path)
+    _run(["--network", "network.jsn", "--ff_input_file", "val.nc", "--ff_output_file", "htkdir", "--ff_output_format", "htk",
+          "--parallel_sequences", "3", "--revert_std", "false", "--feature_period", "12.5", "--ff_output_kind", "9"], str(tmp_path))
+    # the same run as single_csv: the two writers must show the same numbers (to the csv's 6 digits)
+    _run(["--network", "network.jsn", "--ff_input_file", "val.nc", "--ff_output_file", "ff.csv", "--parallel_sequences", "3",
+          "--revert_std", "false"], str(tmp_path))
+    csv_rows = {ln.split(";")[0]: np.array([float(v) for v in ln.split(";")[1:]], np.float32).reshape(-1, 51)
+                for ln in open(tmp_path / "ff.csv").read().splitlines()}
+    want = _oracle_outputs(oracle, cfg, val, weights, 3)
+    assert sorted(os.listdir(tmp_path / "htkdir")) == ["seq%03d.htk" % k for k in range(len(want))]
+    for k, y in enumerate(want):
+        raw = open(tmp_path / "htkdir" / ("seq%03d.htk" % k), "rb").read()
+        assert raw[:12] == struct.pack(">IIHH", len(y), int(12.5 * 1e4), 51 * 4, 9)          # swap32 / swap16 of main.cpp:449-461
+        assert len(raw) == 12 + len(y) * 51 * 4
+        got = np.frombuffer(raw[12:], dtype=">f4").reshape(len(y), 51)
+        assert np.allclose(got, y, rtol=2e-5, atol=1e-9)
+        assert np.allclose(got, csv_rows["seq%03d" % k], rtol=1e-5, atol=1e-12)
+
+
 def _oracle_train_epochs(oracle, net_json, xs, cs, ts, weights, S, lr, mom, epochs):
     """Training epochs of any task (class targets cs or dense targets ts) replayed by the oracle: per-epoch (error / #sequences,
     #correct or None), and the network."""
