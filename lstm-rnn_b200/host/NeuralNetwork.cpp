@@ -122,34 +122,44 @@ void NeuralNetwork::computeForwardPass()
     for (auto &layer : m_layers) layer->computeForwardPass();
 }
 
+// The trainable layer whose backward pass runs last (the first hidden layer): its gradient has nothing left to overlap with.  EVERY
+// rank must route the same layer through the same communicator -- the ranks of an all-reduce meet inside one communicator -- so the
+// backward pass and contributeZeroGradients() (a rank whose shard of a fraction is empty) share this rule.  (They did not at first:
+// C5 at 4 / 8 GPUs, where truncation leaves a ragged last fraction, hung in its first 8-GPU run.)
+const layers::Layer *NeuralNetwork::lastReducedLayer() const
+{
+    for (auto &layer : m_layers) {
+        layers::TrainableLayer *tl = dynamic_cast<layers::TrainableLayer *>(layer.get());
+        if (tl && !tl->weightUpdates().empty()) return layer.get();
+    }
+    return nullptr;
+}
+
+void NeuralNetwork::reduceGradient(layers::Layer *layer, const layers::Layer *last)
+{
+    layers::TrainableLayer *tl = dynamic_cast<layers::TrainableLayer *>(layer);
+    if (!m_comm || !tl || tl->weightUpdates().empty()) return;
+    if (layer == last) check(m_ctx, bl_allreduce_sum_f32_last(m_comm, tl->weightUpdates().data(), tl->weightUpdates().size()));
+    else check(m_ctx, bl_allreduce_sum_f32(m_comm, tl->weightUpdates().data(), tl->weightUpdates().size()));
+}
+
 void NeuralNetwork::computeBackwardPass()
 {
-    // the trainable layer whose backward pass runs last: its gradient has nothing left to overlap with
-    const layers::Layer *lastReduced = nullptr;
-    if (m_comm)
-        for (auto &layer : m_layers) {
-            layers::TrainableLayer *tl = dynamic_cast<layers::TrainableLayer *>(layer.get());
-            if (tl && !tl->weightUpdates().empty()) { lastReduced = layer.get(); break; }
-        }
+    const layers::Layer *last = m_comm ? lastReducedLayer() : nullptr;
     for (auto it = m_layers.rbegin(); it != m_layers.rend(); ++it) {
         (*it)->computeBackwardPass();
-        if (m_comm) {
-            layers::TrainableLayer *tl = dynamic_cast<layers::TrainableLayer *>(it->get());
-            if (tl && !tl->weightUpdates().empty()) {
-                if (it->get() == lastReduced) check(m_ctx, bl_allreduce_sum_f32_last(m_comm, tl->weightUpdates().data(), tl->weightUpdates().size()));
-                else check(m_ctx, bl_allreduce_sum_f32(m_comm, tl->weightUpdates().data(), tl->weightUpdates().size()));
-            }
-        }
+        reduceGradient(it->get(), last);          // as soon as this layer's backward pass is enqueued
     }
 }
 
 void NeuralNetwork::contributeZeroGradients()
 {
+    const layers::Layer *last = m_comm ? lastReducedLayer() : nullptr;
     for (auto it = m_layers.rbegin(); it != m_layers.rend(); ++it) {
         layers::TrainableLayer *tl = dynamic_cast<layers::TrainableLayer *>(it->get());
         if (!tl || tl->weightUpdates().empty()) continue;
         check(m_ctx, bl_memset(m_ctx, tl->weightUpdates().data(), 0, tl->weightUpdates().size() * sizeof(real_t)));
-        if (m_comm) check(m_ctx, bl_allreduce_sum_f32(m_comm, tl->weightUpdates().data(), tl->weightUpdates().size()));
+        reduceGradient(it->get(), last);
     }
 }
 

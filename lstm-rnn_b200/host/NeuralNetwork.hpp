@@ -34,7 +34,7 @@ public:
 
     // data parallelism (no reference counterpart): when a communicator is attached, every trainable
     // layer's weightUpdates() is handed to bl_allreduce_sum_f32 as soon as that layer's backward is enqueued;
-    // joinGradients() completes the reductions (one grouped NCCL call by default, see csrc/comm.cu) before the update.
+    // joinGradients() completes the reductions before the update (schedules: see csrc/comm.cu).
     void setCommunicator(bl_comm *comm) { m_comm = comm; }
     bl_comm *communicator() const { return m_comm; }
     // a rank whose shard of the fraction is empty still has to take part in the reduction, with zero gradients
@@ -43,6 +43,8 @@ public:
     bl_ctx *ctx() const { return m_ctx; }
 
 private:
+    const layers::Layer *lastReducedLayer() const;
+    void reduceGradient(layers::Layer *layer, const layers::Layer *last);
     bl_ctx *m_ctx;
     bl_comm *m_comm;
     std::vector<std::shared_ptr<layers::Layer>> m_layers;

@@ -18,12 +18,12 @@ def run(args):
 bench = json.load(open(os.path.join(src, tag + "_bench_1gpu.json")))
 json.dump(bench, open(os.path.join(dst, tag + "_bench_1gpu.json"), "w"), indent=1)
 shutil.copy(os.path.join(src, tag + "_launches.csv"), os.path.join(dst, tag + "_launches.csv"))
-steps = 10          # bench.py --steps 2 --warmup 3 runs (3 + 2) steps in each of its value and e2e passes before the capture limit
+steps = 10          # bench.py --steps 2 --warmup 3: 4 warm-up steps (the largest fraction first) + 2 steps in each of its value, e2e and timing passes
 head = ("# ncu --metrics gpu__time_duration.sum --clock-control none -c 3000 python bench.py --steps 2 --warmup 3\n"
         "# B200, C2 workload, strict mode. Cold-cache serialised times: compare SHARES with bench.py's kernel_classes, not absolutes.\n"
         "# raw csv: profiles/%s_launches.csv; per-step columns divide by the %d steps captured\n" % (tag, steps))
 open(os.path.join(dst, tag + "_launch_list_summary.txt"), "w").write(head + run(["tools/launch_summary.py", os.path.join(src, tag + "_launches.csv"), str(steps)]))
-fam = {"tmem": "tmem", "registers": "reg", "smem": "persistent"}
+fam = {"tm2": "tm2", "tmem": "tmem", "registers": "reg", "smem": "persistent"}
 kf, kb = fam[bench["config"]["plan"]["fwd_kernel"]], fam[bench["config"]["plan"]["bwd_kernel"]]
 dram = {}
 for name, what in (("fwd", "lstm_fwd_%s_kernel (second BLSTM layer of C2, the T=780 fraction: 78 000 slots)" % kf),
@@ -52,5 +52,5 @@ if "fwd" in dram and "bwd" in dram:
 tr = os.path.join(src, tag + "_recurrent_trace.txt")
 if os.path.exists(tr):
     open(os.path.join(dst, tag + "_recurrent_trace.txt"), "w").write(
-        "# BLSTM_REC_TRACE=1 python tools/trace_recurrent.py 250 100 300 on B200: in-kernel clock64 stamps of lstm_fwd_%s_kernel\n" % kf + open(tr).read())
+        "# BLSTM_REC_TRACE=1 python tools/trace_recurrent.py 250 100 300 on B200: in-kernel clock64 stamps of lstm_fwd_%s_kernel / lstm_bwd_%s_kernel\n" % (kf, kb) + open(tr).read())
 print("profiles/ updated:", sorted(f for f in os.listdir(dst) if f.startswith(tag)))
