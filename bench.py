@@ -380,15 +380,16 @@ def run_ours(args, rank, world, local_rank):
         rec_ms = class_ms[1] + class_ms[2]
         n_launch = class_cnt[1] + class_cnt[2]
         achieved = (fwd_b + bwd_b) / (rec_ms * 1e-3) / 1e9
-        traffic = None
+        traffic = traffic_note = None
         tpath = os.path.join(ROOT, "profiles", "recurrent_traffic.json")
         if os.path.exists(tpath):        # DRAM bytes per slot and unit of layer size from the committed ncu --set full captures
             tj = json.load(open(tpath))
+            traffic_note = "scaled from the ncu --set full captures of " + tj.get("captured_kernels", "the kernels named in `kernel`") + " (profiles/recurrent_traffic.json)"
             traffic = (fwd_b / 40.0 * tj["fwd_dram_bytes_per_slot_per_layer_unit"] + bwd_b / 48.0 * tj["bwd_dram_bytes_per_slot_per_layer_unit"]) / max(n_launch, 1)
         plan = net.plan_info(2)
         kfam = {"tm2": "tm2", "tmem": "tmem", "registers": "reg", "smem": "persistent"}
         roofline = {"kernel": "lstm_fwd_%s_kernel + lstm_bwd_%s_kernel" % (kfam[plan["fwd_kernel"]], kfam[plan["bwd_kernel"]]), "bound": "hbm", "achieved": achieved, "peak": pk["hbm_gbs"], "unit": "GB/s",
-                    "frac": achieved / pk["hbm_gbs"], "peak_source": pk["source"], "traffic": traffic,
+                    "frac": achieved / pk["hbm_gbs"], "peak_source": pk["source"], "traffic": traffic, "traffic_source": traffic_note,
                     "algorithmic_bytes_per_launch": (fwd_b + bwd_b) / max(n_launch, 1), "avg_launch_ms": rec_ms / max(n_launch, 1),
                     "share_of_kernel_time": share[1] + share[2]}
         # inputs + targets (int class or dense row) + one patTypes byte per slot and layer
