@@ -144,6 +144,11 @@ int bl_lstm_debug_trace2(bl_lstm_plan *plan, int backward, int T, long long *hos
 /* Launch geometry chosen for the persistent kernels: out[0..3] = fwd {G seq groups, C cell slices, cells/CTA, smem bytes},
  * out[4..7] = bwd likewise. */
 int bl_lstm_plan_info(const bl_lstm_plan *plan, int *out8);
+/* The geometry the second-generation tensor-memory kernels would get for a layer of H cells per direction, S parallel sequences and
+ * ndir directions on a device with num_sms SMs and smem_cap bytes of opt-in shared memory -- pure host arithmetic, no device needed
+ * (the CPU tests sweep it).  Returns 1 and fills out12 = {G, C, CL, SG, threads, sub-groups per CTA, padded K or R, sequences per
+ * sub-group, W_lo' in shared memory, shared memory bytes, CTAs, exchange words} or returns 0 when these kernels do not fit the layer. */
+int bl_lstm_tm2_geometry(int backward, int H, int S, int ndir, int num_sms, int smem_cap, long long *out12);
 
 /* ------------------------------------------------------------------ feed-forward / softmax layers
  * FeedForwardLayer<Gpu,TActFn>::computeForwardPass (FeedForwardLayer.cu:143-172): Y = act(W^T X + bias*b) for N slots */

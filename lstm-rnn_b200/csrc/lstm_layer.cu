@@ -195,6 +195,15 @@ void bl_lstm_plan_destroy(bl_lstm_plan *pl)
     delete pl;
 }
 
+int bl_lstm_tm2_geometry(int backward, int H, int S, int ndir, int num_sms, int smem_cap, long long *o)
+{
+    bl::RecGeom g;
+    if (H <= 0 || S <= 0 || ndir < 1 || ndir > 2 || !bl::choose_geometry_tm2(backward != 0, H, S, ndir, num_sms, smem_cap, 0, &g)) return 0;
+    o[0] = g.G; o[1] = g.C; o[2] = g.CL; o[3] = g.SG; o[4] = g.NT; o[5] = g.nsub; o[6] = g.Hpad; o[7] = g.Spad; o[8] = g.K4;
+    o[9] = (long long)g.smem; o[10] = (long long)ndir * bl::cdiv(g.G, g.nsub) * g.C; o[11] = (long long)g.xelems;
+    return 1;
+}
+
 int bl_lstm_plan_info(const bl_lstm_plan *pl, int *o)
 {
     // smem is a multiple of 4: the low two bits carry nsub (1, 2, 4 -> 1, 2, 0), or 3 for the register-resident kernels
