@@ -11,7 +11,14 @@ struct Reader {
     std::ifstream f; bool cdf2 = false;
     uint32_t u32() { unsigned char b[4]; f.read((char *)b, 4); if (!f) throw std::runtime_error("truncated NetCDF header"); return (uint32_t)b[0] << 24 | b[1] << 16 | b[2] << 8 | b[3]; }
     uint64_t u64() { uint64_t hi = u32(); return hi << 32 | u32(); }
-    std::string name() { uint32_t n = u32(); std::string s(n, '\0'); f.read(&s[0], n); f.seekg((4 - n % 4) % 4, std::ios::cur); return s; }
+    std::string name()
+    {
+        uint32_t n = u32();
+        if (n > 4096) throw std::runtime_error("bad NetCDF header: name of " + std::to_string(n) + " bytes");
+        std::string s(n, '\0'); f.read(&s[0], n); f.seekg((4 - n % 4) % 4, std::ios::cur);
+        if (!f) throw std::runtime_error("truncated NetCDF header");
+        return s;
+    }
     void skipAttrs()
     {
         uint32_t tag = u32(), n = u32();
@@ -52,7 +59,12 @@ NetCdfFile::NetCdfFile(const std::string &path) : m_path(path), m_numrecs(0), m_
         for (uint32_t i = 0; i < n; ++i) {
             std::string nm = r.name();
             Var v; uint32_t nd = r.u32();
-            for (uint32_t d = 0; d < nd; ++d) v.dimids.push_back((int)r.u32());
+            if (nd > 1024) throw std::runtime_error("bad NetCDF header: variable '" + nm + "' has " + std::to_string(nd) + " dimensions");
+            for (uint32_t d = 0; d < nd; ++d) {
+                const uint32_t id = r.u32();
+                if (id >= m_dimList.size()) throw std::runtime_error("bad NetCDF header: variable '" + nm + "' uses an undefined dimension");
+                v.dimids.push_back((int)id);
+            }
             r.skipAttrs();
             v.type = (int)r.u32(); v.vsize = r.u32(); v.begin = r.cdf2 ? r.u64() : r.u32();
             if (v.type < 1 || v.type > 6) throw std::runtime_error("bad NetCDF variable type");
@@ -131,10 +143,23 @@ std::unique_ptr<DataSet> loadNetCdfDataSet(bl_ctx *ctx, const std::vector<std::s
         int nSeq = nc.dimension("numSeqs");
         nSeq = std::max((int)((real_t)nSeq * fraction), 1);                                                       // DataSet.cpp:514-516
         const std::vector<int> lens = nc.readInts("seqLengths");
+        // the header is not trusted: every variable must hold what the dimensions promise (a truncated or inconsistent file is an error)
+        auto need = [&path](const char *what, size_t have, size_t want) {
+            if (have < want)
+                throw std::runtime_error("Inconsistent NC file '" + path + "': '" + what + "' holds " + std::to_string(have) +
+                                         " values, " + std::to_string(want) + " needed");
+        };
+        if (p <= 0 || o <= 0) throw std::runtime_error("Inconsistent NC file '" + path + "': pattern sizes must be positive");
+        need("seqLengths", lens.size(), (size_t)nSeq);
         size_t frames = 0;
-        for (int i = 0; i < nSeq; ++i) { seqLengths.push_back(lens[i]); frames += (size_t)lens[i]; }
+        for (int i = 0; i < nSeq; ++i) {
+            if (lens[i] <= 0) throw std::runtime_error("Inconsistent NC file '" + path + "': sequence " + std::to_string(i) + " has length " + std::to_string(lens[i]));
+            seqLengths.push_back(lens[i]); frames += (size_t)lens[i];
+        }
         const int tagLen = nc.dimension("maxSeqTagLength");
         const std::vector<char> tagChars = nc.readChars("seqTags");
+        if (tagLen <= 0) throw std::runtime_error("Inconsistent NC file '" + path + "': maxSeqTagLength must be positive");
+        need("seqTags", tagChars.size(), (size_t)nSeq * (size_t)tagLen);
         for (int i = 0; i < nSeq; ++i) {                                                                          // DataSet.cpp:525
             const char *t = tagChars.data() + (size_t)i * tagLen;
             size_t n = 0; while (n < (size_t)tagLen && t[n]) ++n;
@@ -144,9 +169,21 @@ std::unique_ptr<DataSet> loadNetCdfDataSet(bl_ctx *ctx, const std::vector<std::s
             if (nc.hasVariable("outputMeans") && nc.hasVariable("outputStdevs")) { means = nc.readFloats("outputMeans"); stdevs = nc.readFloats("outputStdevs"); }
         }
         const std::vector<float> in = nc.readFloats("inputs");
+        need("inputs", in.size(), frames * (size_t)P);
         inputs.insert(inputs.end(), in.begin(), in.begin() + frames * P);
-        if (cls) { const std::vector<int> tc = nc.readInts("targetClasses"); classes.insert(classes.end(), tc.begin(), tc.begin() + frames); }
-        else { const std::vector<float> tp = nc.readFloats("targetPatterns"); targets.insert(targets.end(), tp.begin(), tp.begin() + frames * O); }
+        if (cls) {
+            const std::vector<int> tc = nc.readInts("targetClasses");
+            need("targetClasses", tc.size(), frames);
+            const int numLabels = nc.dimension("numLabels");
+            for (size_t i = 0; i < frames; ++i)
+                if (tc[i] < 0 || tc[i] >= numLabels)
+                    throw std::runtime_error("Inconsistent NC file '" + path + "': target class " + std::to_string(tc[i]) + " outside [0, " + std::to_string(numLabels) + ")");
+            classes.insert(classes.end(), tc.begin(), tc.begin() + frames);
+        } else {
+            const std::vector<float> tp = nc.readFloats("targetPatterns");
+            need("targetPatterns", tp.size(), frames * (size_t)O);
+            targets.insert(targets.end(), tp.begin(), tp.begin() + frames * O);
+        }
         first = false;
     }
     std::unique_ptr<DataSet> ds(new DataSet(ctx, (int)seqLengths.size(), seqLengths.data(), P, O, inputs.data(),

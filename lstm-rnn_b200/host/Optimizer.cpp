@@ -20,6 +20,7 @@ SteepestDescentOptimizer::SteepestDescentOptimizer(NeuralNetwork &nn, real_t lea
         m_weightDeltas.emplace_back(new device::real_vector(nn.ctx(), n, true));                       // zeros, SteepestDescentOptimizer.cu:105-108
         m_curWeightUpdates.emplace_back(new device::real_vector(nn.ctx(), hybridOnlineBatch ? 0 : n, true));
     }
+    storeWeights();          // best weights = the initial weights until a validation pass says otherwise (Optimizer.cu:106-127)
 }
 
 void SteepestDescentOptimizer::updateWeights()
@@ -161,7 +162,6 @@ void SteepestDescentOptimizer::storeWeights()
 void SteepestDescentOptimizer::restoreWeights()
 {
     bl_ctx *ctx = m_nn.ctx();
-    if (m_bestWeights.empty()) return;
     for (size_t i = 0; i < m_nn.layers().size(); ++i) {
         layers::TrainableLayer *tl = dynamic_cast<layers::TrainableLayer *>(m_nn.layers()[i].get());
         if (tl) check(ctx, bl_memcpy_d2d(ctx, tl->weights().data(), m_bestWeights[i]->data(), tl->weights().size() * sizeof(real_t)));
@@ -250,7 +250,6 @@ template <> real_t checkedGet<real_t>(const helpers::JsonDocument &doc, const ch
 void SteepestDescentOptimizer::exportState(helpers::JsonDocument &doc)
 {
     using helpers::JsonValue;
-    if (m_bestWeights.empty()) storeWeights();                                    // the reference starts with best = initial weights (Optimizer.cu ctor)
     doc.member("optimizer_finished") = JsonValue::makeBool(m_finished);
     doc.member("optimizer_cur_epoch") = JsonValue::makeNumber(m_curEpoch, true);
     doc.member("optimizer_epochs_since_lowest_error") = JsonValue::makeNumber(m_epochsSinceLowestError, true);
@@ -267,7 +266,6 @@ void SteepestDescentOptimizer::exportState(helpers::JsonDocument &doc)
 
 void SteepestDescentOptimizer::importState(const helpers::JsonDocument &doc)
 {
-    if (m_bestWeights.empty()) storeWeights();                                    // allocates the per-layer vectors
     m_finished = checkedGet<bool>(doc, "optimizer_finished");
     m_curEpoch = checkedGet<int>(doc, "optimizer_cur_epoch");
     m_epochsSinceLowestError = checkedGet<int>(doc, "optimizer_epochs_since_lowest_error");

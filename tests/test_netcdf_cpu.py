@@ -93,6 +93,57 @@ def test_netcdf_errors(tmp_path):
         cb.DataSet.from_netcdf(None, p1, 2, fraction=0.0)
 
 
+def _patch(path, old, new):
+    """Overwrites the first occurrence of the big-endian int32 run `old` in a file (a variable's data) by `new`."""
+    raw = bytearray(open(path, "rb").read())
+    key = np.asarray(old, ">i4").tobytes()
+    at = raw.find(key)
+    assert at >= 0 and raw.find(key, at + 1) < 0
+    raw[at:at + len(key)] = np.asarray(new, ">i4").tobytes()
+    open(path, "wb").write(bytes(raw))
+
+
+def test_netcdf_inconsistent_files_are_rejected(tmp_path):
+    """The loader does not trust the header: lengths that overrun the data, non-positive lengths, labels outside the label set and
+    files cut short are clean errors (the reference reads past the end of its buffers on such files, DataSet.cpp:514-560)."""
+    xs, cs, _ = _data(5, 3, 4, True, seed=8)
+    lens = [len(x) for x in xs]
+    good = str(tmp_path / "good.nc")
+    _write_nc(good, xs, cs, labels=4)
+    cb.DataSet.from_netcdf(None, good, 2)
+    # sequence lengths that add up to more frames than the file holds
+    p = str(tmp_path / "overrun.nc"); _write_nc(p, xs, cs, labels=4)
+    _patch(p, lens, [lens[0] + 1000] + lens[1:])
+    with pytest.raises(RuntimeError, match="Inconsistent NC file.*'inputs' holds"):
+        cb.DataSet.from_netcdf(None, p, 2)
+    # a sequence of length 0 / a negative length
+    for bad_len in (0, -3):
+        p = str(tmp_path / ("len%d.nc" % bad_len)); _write_nc(p, xs, cs, labels=4)
+        _patch(p, lens, lens[:2] + [bad_len] + lens[3:])
+        with pytest.raises(RuntimeError, match="sequence 2 has length %d" % bad_len):
+            cb.DataSet.from_netcdf(None, p, 2)
+    # a label outside [0, numLabels)
+    p = str(tmp_path / "label.nc"); _write_nc(p, xs, cs, labels=4)
+    flat = np.concatenate(cs)
+    _patch(p, flat, np.concatenate([flat[:7], [4], flat[8:]]))
+    with pytest.raises(RuntimeError, match="target class 4 outside"):
+        cb.DataSet.from_netcdf(None, p, 2)
+    # a file cut short inside its last variable, and one cut inside the header
+    raw = open(good, "rb").read()
+    p = str(tmp_path / "cut.nc"); open(p, "wb").write(raw[:-40])
+    with pytest.raises(RuntimeError, match="truncated"):
+        cb.DataSet.from_netcdf(None, p, 2)
+    p = str(tmp_path / "cut_header.nc"); open(p, "wb").write(raw[:60])
+    with pytest.raises(RuntimeError, match="truncated|bad NetCDF"):
+        cb.DataSet.from_netcdf(None, p, 2)
+    # only a fraction of the sequences is read: the overrun check follows the sequences actually used
+    p = str(tmp_path / "tail.nc"); _write_nc(p, xs, cs, labels=4)
+    _patch(p, lens, lens[:4] + [lens[4] + 1000])
+    cb.DataSet.from_netcdf(None, p, 2, fraction=0.8)
+    with pytest.raises(RuntimeError, match="Inconsistent NC file"):
+        cb.DataSet.from_netcdf(None, p, 2)
+
+
 REF_NC = "/root/reference/examples/speech_recognition_chime/val_1_speaker.nc"
 
 
