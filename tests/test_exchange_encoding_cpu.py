@@ -83,3 +83,28 @@ def test_delta_operand_scale_keeps_small_deltas_normal():
     back0 = hi0.astype(np.float64) + lo0.astype(np.float64) / 2048.0
     assert np.max(np.abs(back0 - d.astype(np.float64)) / d) > 1e-5        # what the scale avoids
     assert np.max(np.abs(hi.astype(np.float32))) < 65504 and 8192.0 * 1.0 < 65504
+
+
+def test_two_term_step_product_reaches_fp32_accuracy():
+    """W h ~= W_hi h_hi + 2^-11 (W_hi h_lo' + W_lo' h_hi), products of fp16 pairs (exact in fp32) summed in fp32: the scheme of the step GEMM
+    (32 kind::f16 MMAs per 256-wide step), emulated here; tools/micro/tcgen05_f16_step.cu measured the same on the tensor cores
+    (profiles/r02_probes.txt: 3.9e-7 .. 5.1e-7 of max|W h|, the reference's own serial fp32 sum 3.8e-7 .. 5.0e-7)."""
+    rng = np.random.default_rng(5)
+    for scale in (1e-4, 0.1, 3.0):
+        W = rng.uniform(-scale, scale, (128, 256)).astype(np.float32)
+        h = (np.tanh(rng.standard_normal((256, 16))) * rng.uniform(0, 1, (256, 16))).astype(np.float32)
+        ref = W.astype(np.float64) @ h.astype(np.float64)
+        # per-CTA power-of-two weight scale (t2_slice_scale) is only needed beyond fp16 range; these weights are inside it
+        Whi, Wlo = split16(W)
+        hhi, hlo = split16(h)
+        f = lambda a: a.astype(np.float32)                                            # noqa: E731
+        d0 = f(Whi) @ f(hhi)
+        d1 = f(Whi) @ f(hlo) + f(Wlo) @ f(hhi)
+        full = d0 + d1 * np.float32(1.0 / 2048.0)
+        denom = np.abs(ref).max()
+        assert np.abs(full - ref).max() / denom < 1.5e-6
+        assert np.abs(d0 - ref).max() / denom > 5e-5                                   # one term alone is an 11-bit product
+        serial = np.zeros((128, 16), np.float32)
+        for k in range(256):                                                          # the reference's own order: one fp32 sum over k
+            serial += W[:, k:k + 1] * h[k:k + 1, :]
+        assert np.abs(full - ref).max() <= 4 * np.abs(serial - ref).max()
