@@ -300,10 +300,9 @@ int run(const Options &opt)
                                                                               train ? truncSeq : 0, train, rank, world);
         // context windows and the target lag apply to every set (the reference reads them from the Configuration singleton)
         ds->setContext((int)opt.num("input_left_context"), (int)opt.num("input_right_context"), (int)opt.num("output_time_lag"));
-        if (train) {
-            ds->setShuffling(opt.flag("shuffle_fractions"), opt.flag("shuffle_sequences"), blob.seed);
+        if (train) ds->setShuffling(opt.flag("shuffle_fractions"), opt.flag("shuffle_sequences"), blob.seed);
+        if (train || !training)          // the reference also adds the input noise to the feed forward input set (main.cpp:610-614)
             ds->setInputNoise((real_t)opt.num("input_noise_sigma"), blob.seed);
-        }
         if (chief) {
             std::printf("done.\nLoaded fraction:  %d%%\nSequences:        %d\nSequence lengths: %d..%d\nTotal timesteps:  %d\n\n",
                         (int)(100 * (fracKey ? opt.num(fracKey) : 1)), ds->totalSequences(), ds->minSeqLength(), ds->maxSeqLength(), ds->totalTimesteps());
