@@ -137,9 +137,10 @@ int bl_lstm_get_internal(bl_lstm_plan *plan, int dir, int which, int T, float *d
 /* Tuning aid (BLSTM_REC_TRACE=1 at plan creation): per-CTA, per-step clock64 stamps of the forward persistent kernel,
  * [rows][T][6] = {step start, counter seen, exchange copied, GEMM done, gate math done, published}. */
 int bl_lstm_debug_trace(bl_lstm_plan *plan, int T, long long *host_dst, int *rows);
-/* The same for the second-generation tensor-memory kernels, forward (backward = 0) or BPTT (1): [rows][T][8] =
- * {step start, exchange polled, MMAs complete | deltas in the B tile, gate math done | MMAs complete, exchange stored, results stored,
- *  control warp: MMAs issued, control warp: re-arm fenced}. */
+/* The same for the second-generation tensor-memory kernels, forward (backward = 0) or BPTT (1): [rows][T][8], rows = CTAs x
+ * sub-groups.  Forward: {step start, exchange polled, MMAs complete, accumulator staged, gate math done, exchange word stored,
+ * control thread: first K-block ready, control thread: MMAs issued}; BPTT: {step start, partials polled, deltas in the B tile,
+ * MMAs complete, partials stored, -, control thread: B tile ready, control thread: MMAs issued}. */
 int bl_lstm_debug_trace2(bl_lstm_plan *plan, int backward, int T, long long *host_dst, int *rows);
 /* Launch geometry chosen for the persistent kernels: out[0..3] = fwd {G seq groups, C cell slices, cells/CTA, smem bytes},
  * out[4..7] = bwd likewise. */

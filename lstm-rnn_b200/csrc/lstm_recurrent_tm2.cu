@@ -1,7 +1,7 @@
 // Persistent recurrent kernels, second tensor-memory generation ("tm2").  Same decomposition as lstm_recurrent_tmem.cu -- CTA (d, g, c)
 // owns CL cells of direction d for the SG sequences of group g, its slice of the recurrent weights stays in TENSOR MEMORY for the whole
 // pass and the per-timestep product runs on tcgen05.mma -- but the per-step protocol is rebuilt around what the round-2 probes measured
-// (tools/micro/exchange_probe.cu, gate_math_probe.cu, tcgen05_f16_step.cu; profiles/r02_probes.txt, r02_trace_*.txt):
+// (tools/micro/exchange_probe.cu, gate_math_probe.cu, tcgen05_f16_step.cu; profiles/r02_probes.txt, r02_recurrent_trace.txt):
 //
 //  * in-band exchange: no step counter, no fence + atomic publish, no re-arming.  Every exchanged 32-bit word carries a one-bit step
 //    tag and consumers poll the WORDS themselves (ld.relaxed.gpu) until the tag is the one of the step they wait for; two buffers per
