@@ -173,3 +173,26 @@ def test_command_line_front_end_without_gpu(tmp_path):
     if not torch.cuda.is_available():
         r = subprocess.run([exe, "--train", "true", "--train_file", "x.nc"], capture_output=True, text=True)
         assert r.returncode == 2 and "FAILED" in r.stdout and "no CPU fallback" in r.stdout
+
+
+def test_product_path_never_touches_the_oracle():
+    """oracle/ is test infrastructure: nothing under lstm-rnn_b200/ (kernels, host layer, Python glue, Makefile) and nothing in include/ may
+    name it, and bench.py only reaches it from its cpu_baseline / --impl reference legs."""
+    import re
+    root = os.path.join(os.path.dirname(__file__), "..")
+    bad = []
+    for base in ("lstm-rnn_b200", "include"):
+        for d, _, files in os.walk(os.path.join(root, base)):
+            for f in files:
+                if f.endswith((".cu", ".cuh", ".cpp", ".hpp", ".h", ".py", "Makefile")):
+                    text = open(os.path.join(d, f), errors="replace").read()
+                    if re.search(r"^\s*(import|from)\s+oracle|liboracle|libcurrennt_ref|oracle/|_ref/", text, re.M):
+                        bad.append(os.path.join(d, f))
+    assert not bad, bad
+    # bench.py: every mention of the oracle sits inside the two CPU-baseline helpers (the timed GPU arm, run_ours, has none)
+    bench = open(os.path.join(root, "bench.py")).read()
+    ours = bench[bench.index("def run_ours("):bench.index("def main(")]
+    body = "\n".join(line for line in ours.splitlines() if not line.strip().startswith("#"))
+    assert not re.search(r"pyoracle|liboracle|libcurrennt_ref|from oracle|import oracle", body)
+    for fn in ("cpu_reference_rate", "cpu_reference_best"):
+        assert "def %s(" % fn in bench
